@@ -1,0 +1,120 @@
+"""ctypes binding of the C ABI in ``include/hsm.h`` (``libhsm_b200.so``).
+
+The shared library is built in-tree by ``build_library()`` (nvcc, sm_100a) and
+loaded from the package directory.  There is no CPU fallback: if the library is
+missing and cannot be built, or no GPU is usable, the calls raise.
+"""
+import ctypes
+import os
+import shutil
+import subprocess
+
+_PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+_CSRC = os.path.join(_PKG_DIR, "csrc")
+LIB_PATH = os.path.join(_PKG_DIR, "libhsm_b200.so")
+HEADER_PATH = os.path.join(os.path.dirname(_PKG_DIR), "include", "hsm.h")
+
+NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+              "-Xcompiler", "-fPIC", "-shared"]
+
+# status codes / enums of include/hsm.h
+OK, ERR_ARG, ERR_CUDA, ERR_STATE = 0, 1, 2, 3
+F32, F64, I32, I64 = 0, 1, 2, 3
+PRIOR_NONE, PRIOR_CONST, PRIOR_ADAPTIVE, PRIOR_CONST_F64 = 0, 1, 2, 3
+OPT_ALGORITHM, OPT_BAND_ROWS, OPT_DATA_TERM = 0, 1, 2
+OPT_VALID_LO, OPT_VALID_HI, OPT_OUT_LO, OPT_OUT_HI, OPT_FAST_DIV = 3, 4, 5, 6, 7
+PLANES = ("south", "west", "north", "east", "data")      # reference dict order, mrf.py:15-19
+
+
+class Stats(ctypes.Structure):
+    _fields_ = [("kernel_launches", ctypes.c_uint64), ("iteration_launches", ctypes.c_uint64),
+                ("iterations", ctypes.c_uint64), ("iteration_ms", ctypes.c_double),
+                ("device_bytes", ctypes.c_uint64)]
+
+
+def _sources():
+    return [os.path.join(_CSRC, f) for f in sorted(os.listdir(_CSRC)) if f.endswith((".cu", ".cuh"))] \
+        + [HEADER_PATH]
+
+
+def library_is_stale():
+    if not os.path.exists(LIB_PATH):
+        return True
+    built = os.path.getmtime(LIB_PATH)
+    return any(os.path.getmtime(src) > built for src in _sources())
+
+
+def build_library(force=False, verbose=False):
+    """Compile csrc/*.cu into libhsm_b200.so for sm_100a (works without a GPU)."""
+    if not force and not library_is_stale():
+        return LIB_PATH
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        raise RuntimeError("nvcc not found: cannot build %s" % LIB_PATH)
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+          ["-o", LIB_PATH, os.path.join(_CSRC, "hsm_api.cu")]
+    proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, universal_newlines=True)
+    if proc.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + proc.stdout)
+    if verbose:
+        print(proc.stdout)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    """The loaded library (built first if it is missing or older than its sources)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if library_is_stale():
+        build_library()
+    handle = ctypes.CDLL(LIB_PATH)
+    vp, ci, cf, cd, sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_double, ctypes.c_size_t
+    sig = {
+        "hsm_version": ([], ci),
+        "hsm_last_error": ([], ctypes.c_char_p),
+        "hsm_device_count": ([ctypes.POINTER(ci)], ci),
+        "hsm_create": ([ci, ci, ci, ci, ci, ctypes.POINTER(vp)], ci),
+        "hsm_destroy": ([vp], ci),
+        "hsm_set_stream": ([vp, vp], ci),
+        "hsm_set_option": ([vp, ci, ci], ci),
+        "hsm_get_option": ([vp, ci, ctypes.POINTER(ci)], ci),
+        "hsm_device_bytes": ([ci, ci, ci, ci, ctypes.POINTER(sz)], ci),
+        "hsm_init_fields": ([vp, ci, vp, vp, ci, vp, ci, ci, cf, cd, ci, ci], ci),
+        "hsm_iterate": ([vp, ci, ci], ci),
+        "hsm_readout": ([vp, vp, ci, ci], ci),
+        "hsm_lbp": ([vp, ci, vp, vp, ci, vp, ci, ci, cf, cd, ci, vp, ci, ci], ci),
+        "hsm_sync": ([vp], ci),
+        "hsm_get_plane": ([vp, ci, ci, vp], ci),
+        "hsm_get_energy": ([vp, ci, vp], ci),
+        "hsm_set_plane": ([vp, ci, ci, vp], ci),
+        "hsm_halo_floats": ([vp, ctypes.POINTER(sz)], ci),
+        "hsm_halo_pack": ([vp, vp, vp], ci),
+        "hsm_halo_unpack": ([vp, vp, vp], ci),
+        "hsm_get_stats": ([vp, ctypes.POINTER(Stats)], ci),
+        "hsm_reset_stats": ([vp], ci),
+        "hsm_selftest_division": ([vp, vp, sz, ctypes.POINTER(ctypes.c_uint64)], ci),
+        "hsm_host_alloc": ([sz, ctypes.POINTER(vp)], ci),
+        "hsm_host_free": ([vp], ci),
+    }
+    for name, (argtypes, restype) in sig.items():
+        fn = getattr(handle, name)
+        fn.argtypes, fn.restype = argtypes, restype
+    handle._hsm_symbols = tuple(sig)
+    _lib = handle
+    return _lib
+
+
+def check(status):
+    """Map a C status to the reference's error behaviour:
+    shape-contract violations -> ValueError, CUDA/state errors -> RuntimeError (which
+    hybrid_stereo.py:141-145 catches to fall back from online to offline mode)."""
+    if status == OK:
+        return
+    message = lib().hsm_last_error().decode("utf-8", "replace")
+    if status == ERR_ARG:
+        raise ValueError(message)
+    raise RuntimeError(message)

@@ -1,0 +1,748 @@
+// Host side of the C ABI declared in include/hsm.h.
+//
+// One hsm_matcher owns: the five planes of the reference's StereoMRF
+// (mrf.py:15-19) in the device layout described in kernels.cuh, with the west /
+// north / east planes double-buffered (the fused iteration reads the old state
+// of neighbouring pixels, so it cannot update in place); the float32 images and
+// the int32 prior labels; staging space for callers' float64 / int64 arrays.
+// Everything is allocated lazily on the first compute call (fork safety).
+#include "../../include/hsm.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+
+using namespace hsm;
+
+namespace {
+
+thread_local std::string g_error;
+
+int fail(int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_error = buf;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                            \
+    do {                                                                                          \
+        cudaError_t err__ = (expr);                                                               \
+        if (err__ != cudaSuccess)                                                                 \
+            return fail(HSM_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(err__),  \
+                        __FILE__, __LINE__);                                                      \
+    } while (0)
+
+#define HSM_TRY(expr)                    \
+    do {                                 \
+        int rc__ = (expr);               \
+        if (rc__ != HSM_OK) return rc__; \
+    } while (0)
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+size_t dtype_size(int dtype)
+{
+    switch (dtype) {
+        case HSM_F32: case HSM_I32: return 4;
+        case HSM_F64: case HSM_I64: return 8;
+        default: return 0;
+    }
+}
+
+// Lane configuration for a disparity range: LPP lanes per pixel, VPL float4 per lane,
+// NT threads per CTA of the fused kernel.
+struct LaneCfg {
+    int lpp, vpl, nt;
+};
+
+bool lane_cfg(int D, LaneCfg *c)
+{
+    if (D <= 16) *c = {4, 1, 256};
+    else if (D <= 32) *c = {8, 1, 256};
+    else if (D <= 64) *c = {16, 1, 512};
+    else if (D <= 128) *c = {32, 1, 512};
+    else if (D <= 256) *c = {32, 2, 512};
+    else if (D <= 512) *c = {32, 4, 256};
+    else return false;
+    return true;
+}
+
+// Run `body` with LPP, VPL, NT as compile-time constants.
+#define HSM_DISPATCH(cfg, ...)                                                     \
+    do {                                                                           \
+        if ((cfg).lpp == 4) { constexpr int LPP = 4, VPL = 1, NT = 256; __VA_ARGS__ }          \
+        else if ((cfg).lpp == 8) { constexpr int LPP = 8, VPL = 1, NT = 256; __VA_ARGS__ }     \
+        else if ((cfg).lpp == 16) { constexpr int LPP = 16, VPL = 1, NT = 512; __VA_ARGS__ }   \
+        else if ((cfg).vpl == 1) { constexpr int LPP = 32, VPL = 1, NT = 512; __VA_ARGS__ }    \
+        else if ((cfg).vpl == 2) { constexpr int LPP = 32, VPL = 2, NT = 512; __VA_ARGS__ }    \
+        else { constexpr int LPP = 32, VPL = 4, NT = 256; __VA_ARGS__ }                        \
+    } while (0)
+
+}  // namespace
+
+struct hsm_matcher {
+    int H = 0, W = 0, D = 0, Dp = 0, cap = 0, device = 0;
+    LaneCfg cfg{};
+    bool ready = false;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    void *arena = nullptr;
+    size_t arena_bytes = 0;
+    float *S = nullptr, *Wm[2] = {nullptr, nullptr}, *Nm[2] = {nullptr, nullptr}, *Em[2] = {nullptr, nullptr};
+    float *Dt = nullptr;
+    float *L = nullptr, *R = nullptr;
+    int *P = nullptr;
+    char *stage[3] = {nullptr, nullptr, nullptr};
+    long long *labels = nullptr;
+    int cur = 0;          // which of the double buffers holds the current W, N, E
+    int frames = 0;       // frames of the current batch
+    bool have_fields = false, have_prior = false, dt_valid = false, s_valid = true;
+    Blend blend{kPriorNone, 0.0f, 0.0};
+    // options
+    int algorithm = 1, band_rows = 0, data_term = 1;
+    int vlo = 0, vhi = 0, olo = 0, ohi = 0;
+    // statistics
+    hsm_stats stats{};
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending, pool;
+};
+
+namespace {
+
+size_t plane_floats(const hsm_matcher *m) { return (size_t)m->cap * m->H * m->W * m->Dp; }
+size_t image_elems(const hsm_matcher *m) { return (size_t)m->cap * m->H * m->W; }
+
+size_t arena_layout(hsm_matcher *m, bool assign)
+{
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        size_t at = off;
+        off = align_up(off + bytes, 256);
+        return at;
+    };
+    char *base = (char *)m->arena;
+    const size_t pb = plane_floats(m) * sizeof(float), ib = image_elems(m);
+    size_t o;
+    o = take(pb); if (assign) m->S = (float *)(base + o);
+    for (int i = 0; i < 2; ++i) {
+        o = take(pb); if (assign) m->Wm[i] = (float *)(base + o);
+        o = take(pb); if (assign) m->Nm[i] = (float *)(base + o);
+        o = take(pb); if (assign) m->Em[i] = (float *)(base + o);
+    }
+    o = take(pb); if (assign) m->Dt = (float *)(base + o);
+    o = take(ib * 4); if (assign) m->L = (float *)(base + o);
+    o = take(ib * 4); if (assign) m->R = (float *)(base + o);
+    o = take(ib * 4); if (assign) m->P = (int *)(base + o);
+    for (int i = 0; i < 3; ++i) { o = take(ib * 8); if (assign) m->stage[i] = base + o; }
+    o = take(ib * 8); if (assign) m->labels = (long long *)(base + o);
+    return off;
+}
+
+int ensure_ready(hsm_matcher *m)
+{
+    CUDA_TRY(cudaSetDevice(m->device));
+    if (m->ready) return HSM_OK;
+    if (m->stream == nullptr) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+        m->own_stream = true;
+    }
+    m->arena_bytes = arena_layout(m, false);
+    CUDA_TRY(cudaMalloc(&m->arena, m->arena_bytes));
+    arena_layout(m, true);
+    // message planes start at zero (mrf.py:15-19); the data plane is defined by init_fields
+    CUDA_TRY(cudaMemsetAsync(m->arena, 0, m->arena_bytes, m->stream));
+    m->stats.device_bytes = m->arena_bytes;
+    m->ready = true;
+    return HSM_OK;
+}
+
+Geo geometry(const hsm_matcher *m)
+{
+    Geo g;
+    g.H = m->H; g.W = m->W; g.D = m->D; g.Dp = m->Dp;
+    g.vlo = m->vlo; g.vhi = m->vhi;
+    g.plane_stride = (size_t)m->H * m->W * m->Dp;
+    g.image_stride = (size_t)m->H * m->W;
+    return g;
+}
+
+int pixel_grid(const hsm_matcher *m, int lpp)
+{
+    const size_t groups = 256 / lpp;
+    const size_t n_pix = (size_t)m->frames * m->H * m->W;
+    size_t blocks = (n_pix + groups - 1) / groups;
+    return (int)std::min<size_t>(blocks, (size_t)148 * 64);
+}
+
+int check_launch(hsm_matcher *m, const char *what)
+{
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return fail(HSM_ERR_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(err));
+    m->stats.kernel_launches++;
+    return HSM_OK;
+}
+
+int ensure_data_plane(hsm_matcher *m)
+{
+    if (m->dt_valid) return HSM_OK;
+    if (!m->have_fields) {      // never initialised: the data plane is all zero (mrf.py:19)
+        CUDA_TRY(cudaMemsetAsync(m->Dt, 0, plane_floats(m) * sizeof(float), m->stream));
+        m->dt_valid = true;
+        return HSM_OK;
+    }
+    const Geo g = geometry(m);
+    const int *prior = m->have_prior ? m->P : nullptr;
+    HSM_DISPATCH(m->cfg, {
+        (void)NT;
+        k_cost_volume<LPP, VPL><<<pixel_grid(m, LPP), 256, 0, m->stream>>>(g, m->frames, m->L, m->R, prior,
+                                                                          m->blend, m->Dt);
+    });
+    HSM_TRY(check_launch(m, "k_cost_volume"));
+    m->dt_valid = true;
+    return HSM_OK;
+}
+
+int resolve_events(hsm_matcher *m)
+{
+    for (auto &pr : m->pending) {
+        CUDA_TRY(cudaEventSynchronize(pr.second));
+        float ms = 0.0f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, pr.first, pr.second));
+        m->stats.iteration_ms += ms;
+        m->pool.push_back(pr);
+    }
+    m->pending.clear();
+    return HSM_OK;
+}
+
+int copy_in(hsm_matcher *m, void *dst, const void *src, size_t bytes, int on_device)
+{
+    CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
+                             m->stream));
+    return HSM_OK;
+}
+
+int load_image(hsm_matcher *m, float *dst, const void *src, int dtype, int slot, size_t n, int on_device)
+{
+    if (dtype == HSM_F32) return copy_in(m, dst, src, n * 4, on_device);
+    const void *dev_src = src;
+    if (!on_device) {
+        HSM_TRY(copy_in(m, m->stage[slot], src, n * 8, 0));
+        dev_src = m->stage[slot];
+    }
+    const int blocks = (int)std::min<size_t>((n + 255) / 256, (size_t)148 * 16);
+    k_to_f32<double><<<blocks, 256, 0, m->stream>>>((const double *)dev_src, dst, n);
+    return check_launch(m, "k_to_f32");
+}
+
+int load_prior(hsm_matcher *m, const void *src, int dtype, size_t n, int on_device)
+{
+    const void *dev_src = src;
+    if (!on_device) {
+        HSM_TRY(copy_in(m, m->stage[2], src, n * dtype_size(dtype), 0));
+        dev_src = m->stage[2];
+    }
+    const int blocks = (int)std::min<size_t>((n + 255) / 256, (size_t)148 * 16);
+    switch (dtype) {
+        case HSM_F32: k_prior_labels<float><<<blocks, 256, 0, m->stream>>>((const float *)dev_src, m->P, n, m->D); break;
+        case HSM_F64: k_prior_labels<double><<<blocks, 256, 0, m->stream>>>((const double *)dev_src, m->P, n, m->D); break;
+        case HSM_I32: k_prior_labels<int><<<blocks, 256, 0, m->stream>>>((const int *)dev_src, m->P, n, m->D); break;
+        case HSM_I64: k_prior_labels<long long><<<blocks, 256, 0, m->stream>>>((const long long *)dev_src, m->P, n, m->D); break;
+        default: return fail(HSM_ERR_ARG, "unknown prior dtype %d", dtype);
+    }
+    return check_launch(m, "k_prior_labels");
+}
+
+int choose_band_rows(const hsm_matcher *m, int strips)
+{
+    const int rows = m->ohi - m->olo + 1;
+    if (m->band_rows > 0) return std::min(m->band_rows, rows);
+    // aim for ~8 CTAs per SM over the whole launch, bands of at least 12 rows (2 halo rows per band)
+    const long target = 148L * 8;
+    const long per_band = (long)strips * m->frames;
+    long bands = (target + per_band - 1) / per_band;
+    bands = std::max(1L, std::min<long>(bands, std::max(1, rows / 12)));
+    return (int)((rows + bands - 1) / bands);
+}
+
+template <int LPP, int VPL, int NT>
+int launch_fused(hsm_matcher *m, bool store_s)
+{
+    const Geo g = geometry(m);
+    constexpr int TX = NT / LPP - 2;
+    const int strips = (m->W + TX - 1) / TX;
+    IterArgs a;
+    a.Win = m->Wm[m->cur]; a.Nin = m->Nm[m->cur]; a.Ein = m->Em[m->cur];
+    a.Wout = m->Wm[m->cur ^ 1]; a.Nout = m->Nm[m->cur ^ 1]; a.Eout = m->Em[m->cur ^ 1];
+    a.Sout = m->S;
+    a.Dt = m->Dt; a.L = m->L; a.R = m->R; a.P = m->have_prior ? m->P : nullptr;
+    a.blend = m->blend;
+    a.olo = m->olo; a.ohi = m->ohi;
+    a.band_rows = choose_band_rows(m, strips);
+    const int bands = (m->ohi - m->olo + 1 + a.band_rows - 1) / a.band_rows;
+    dim3 grid(strips, bands, m->frames);
+    const bool dt_load = (m->data_term == 0);
+    const bool full = (m->D == 4 * LPP * VPL);
+#define HSM_LAUNCH_FUSED(S, T, F) k_iter_fused<LPP, VPL, NT, S, T, F><<<grid, NT, 0, m->stream>>>(g, a)
+    if (full) {
+        if (store_s) { if (dt_load) HSM_LAUNCH_FUSED(true, true, true); else HSM_LAUNCH_FUSED(true, false, true); }
+        else { if (dt_load) HSM_LAUNCH_FUSED(false, true, true); else HSM_LAUNCH_FUSED(false, false, true); }
+    } else {
+        if (store_s) { if (dt_load) HSM_LAUNCH_FUSED(true, true, false); else HSM_LAUNCH_FUSED(true, false, false); }
+        else { if (dt_load) HSM_LAUNCH_FUSED(false, true, false); else HSM_LAUNCH_FUSED(false, false, false); }
+    }
+#undef HSM_LAUNCH_FUSED
+    HSM_TRY(check_launch(m, "k_iter_fused"));
+    m->stats.iteration_launches++;
+    m->cur ^= 1;
+    return HSM_OK;
+}
+
+int launch_directional(hsm_matcher *m)
+{
+    const Geo g = geometry(m);
+    float *S = m->S, *Wc = m->Wm[m->cur], *Nc = m->Nm[m->cur], *Ec = m->Em[m->cur];
+    HSM_DISPATCH(m->cfg, {
+        (void)NT;
+        const int grid = pixel_grid(m, LPP);
+        k_sweep<LPP, VPL><<<grid, 256, 0, m->stream>>>(g, m->frames, S, Wc, Nc, Ec, m->Dt, +1, 0);
+        HSM_TRY(check_launch(m, "k_sweep south"));
+        k_sweep<LPP, VPL><<<grid, 256, 0, m->stream>>>(g, m->frames, Wc, S, Nc, Ec, m->Dt, 0, -1);
+        HSM_TRY(check_launch(m, "k_sweep west"));
+        k_sweep<LPP, VPL><<<grid, 256, 0, m->stream>>>(g, m->frames, Nc, S, Wc, Ec, m->Dt, -1, 0);
+        HSM_TRY(check_launch(m, "k_sweep north"));
+        k_sweep<LPP, VPL><<<grid, 256, 0, m->stream>>>(g, m->frames, Ec, S, Wc, Nc, m->Dt, 0, +1);
+        HSM_TRY(check_launch(m, "k_sweep east"));
+    });
+    m->stats.iteration_launches += 4;
+    return HSM_OK;
+}
+
+int check_frame(const hsm_matcher *m, int frame, int which, int n_planes)
+{
+    if (!m) return fail(HSM_ERR_ARG, "null matcher");
+    if (frame < 0 || frame >= m->cap) return fail(HSM_ERR_ARG, "frame %d outside capacity %d", frame, m->cap);
+    if (which < 0 || which >= n_planes) return fail(HSM_ERR_ARG, "plane index %d out of range", which);
+    return HSM_OK;
+}
+
+float *plane_ptr(hsm_matcher *m, int which)
+{
+    switch (which) {
+        case 0: return m->S;
+        case 1: return m->Wm[m->cur];
+        case 2: return m->Nm[m->cur];
+        case 3: return m->Em[m->cur];
+        default: return m->Dt;
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int hsm_version(void) { return 100; }
+
+const char *hsm_last_error(void) { return g_error.c_str(); }
+
+int hsm_device_count(int *count)
+{
+    if (!count) return fail(HSM_ERR_ARG, "null count");
+    CUDA_TRY(cudaGetDeviceCount(count));
+    return HSM_OK;
+}
+
+int hsm_create(int rows, int cols, int n_levels, int capacity, int device, hsm_matcher **out)
+{
+    if (!out) return fail(HSM_ERR_ARG, "null output handle");
+    *out = nullptr;
+    if (rows < 1 || cols < 1 || n_levels < 1 || capacity < 1)
+        return fail(HSM_ERR_ARG, "rows, cols, n_levels and capacity must be positive (got %d, %d, %d, %d)", rows,
+                    cols, n_levels, capacity);
+    if (n_levels > cols + 1)
+        return fail(HSM_ERR_ARG, "n_levels %d > cols + 1 = %d: the reference cannot slice such a pair (mrf.py:55)",
+                    n_levels, cols + 1);
+    LaneCfg cfg;
+    if (!lane_cfg(n_levels, &cfg)) return fail(HSM_ERR_ARG, "n_levels %d > 512 is not supported", n_levels);
+    if (capacity > 65535) return fail(HSM_ERR_ARG, "capacity %d > 65535", capacity);
+    hsm_matcher *m = new hsm_matcher();
+    m->H = rows; m->W = cols; m->D = n_levels; m->Dp = (n_levels + 3) / 4 * 4;
+    m->cap = capacity; m->device = device; m->cfg = cfg;
+    m->vlo = 0; m->vhi = rows - 1; m->olo = 0; m->ohi = rows - 1;
+    m->frames = 0;
+    *out = m;
+    return HSM_OK;
+}
+
+int hsm_destroy(hsm_matcher *m)
+{
+    if (!m) return HSM_OK;
+    if (m->ready) {
+        cudaSetDevice(m->device);
+        cudaStreamSynchronize(m->stream);
+        for (auto &pr : m->pending) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+        for (auto &pr : m->pool) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+        cudaFree(m->arena);
+        if (m->own_stream) cudaStreamDestroy(m->stream);
+    }
+    delete m;
+    return HSM_OK;
+}
+
+int hsm_set_stream(hsm_matcher *m, void *cuda_stream)
+{
+    if (!m) return fail(HSM_ERR_ARG, "null matcher");
+    if (m->ready && m->own_stream) {
+        CUDA_TRY(cudaSetDevice(m->device));
+        CUDA_TRY(cudaStreamSynchronize(m->stream));
+        CUDA_TRY(cudaStreamDestroy(m->stream));
+    }
+    m->stream = (cudaStream_t)cuda_stream;
+    m->own_stream = false;
+    if (m->ready && m->stream == nullptr) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+        m->own_stream = true;
+    }
+    return HSM_OK;
+}
+
+int hsm_set_option(hsm_matcher *m, int key, int value)
+{
+    if (!m) return fail(HSM_ERR_ARG, "null matcher");
+    switch (key) {
+        case HSM_OPT_ALGORITHM:
+            if (value != 0 && value != 1) return fail(HSM_ERR_ARG, "algorithm must be 0 or 1");
+            m->algorithm = value; return HSM_OK;
+        case HSM_OPT_BAND_ROWS:
+            if (value < 0) return fail(HSM_ERR_ARG, "band_rows must be >= 0");
+            m->band_rows = value; return HSM_OK;
+        case HSM_OPT_DATA_TERM:
+            if (value != 0 && value != 1) return fail(HSM_ERR_ARG, "data_term must be 0 or 1");
+            m->data_term = value; return HSM_OK;
+        case HSM_OPT_VALID_LO: case HSM_OPT_VALID_HI: case HSM_OPT_OUT_LO: case HSM_OPT_OUT_HI:
+            if (value < 0 || value >= m->H) return fail(HSM_ERR_ARG, "row %d outside [0, %d)", value, m->H);
+            if (key == HSM_OPT_VALID_LO) m->vlo = value;
+            else if (key == HSM_OPT_VALID_HI) m->vhi = value;
+            else if (key == HSM_OPT_OUT_LO) m->olo = value;
+            else m->ohi = value;
+            return HSM_OK;
+        case HSM_OPT_FAST_DIV:
+            return HSM_OK;   // reserved; the division is always correctly rounded
+        default: return fail(HSM_ERR_ARG, "unknown option %d", key);
+    }
+}
+
+int hsm_get_option(hsm_matcher *m, int key, int *value)
+{
+    if (!m || !value) return fail(HSM_ERR_ARG, "null argument");
+    switch (key) {
+        case HSM_OPT_ALGORITHM: *value = m->algorithm; return HSM_OK;
+        case HSM_OPT_BAND_ROWS: *value = m->band_rows; return HSM_OK;
+        case HSM_OPT_DATA_TERM: *value = m->data_term; return HSM_OK;
+        case HSM_OPT_VALID_LO: *value = m->vlo; return HSM_OK;
+        case HSM_OPT_VALID_HI: *value = m->vhi; return HSM_OK;
+        case HSM_OPT_OUT_LO: *value = m->olo; return HSM_OK;
+        case HSM_OPT_OUT_HI: *value = m->ohi; return HSM_OK;
+        case HSM_OPT_FAST_DIV: *value = 0; return HSM_OK;
+        default: return fail(HSM_ERR_ARG, "unknown option %d", key);
+    }
+}
+
+int hsm_device_bytes(int rows, int cols, int n_levels, int capacity, size_t *bytes)
+{
+    if (!bytes) return fail(HSM_ERR_ARG, "null bytes");
+    hsm_matcher tmp;
+    tmp.H = rows; tmp.W = cols; tmp.D = n_levels; tmp.Dp = (n_levels + 3) / 4 * 4; tmp.cap = capacity;
+    *bytes = arena_layout(&tmp, false);
+    return HSM_OK;
+}
+
+int hsm_init_fields(hsm_matcher *m, int n_frames, const void *left, const void *right, int image_dtype,
+                    const void *prior, int prior_dtype, int prior_mode, float keep_f32, double keep_f64,
+                    int reinit_messages, int on_device)
+{
+    if (!m) return fail(HSM_ERR_ARG, "null matcher");
+    if (!left || !right) return fail(HSM_ERR_ARG, "null image pointer");
+    if (n_frames < 1 || n_frames > m->cap)
+        return fail(HSM_ERR_ARG, "n_frames %d outside [1, capacity %d]", n_frames, m->cap);
+    if (image_dtype != HSM_F32 && image_dtype != HSM_F64)
+        return fail(HSM_ERR_ARG, "images must be float32 or float64 (dtype code %d)", image_dtype);
+    if (prior_mode < HSM_PRIOR_NONE || prior_mode > HSM_PRIOR_CONST_F64)
+        return fail(HSM_ERR_ARG, "unknown prior mode %d", prior_mode);
+    if (prior && dtype_size(prior_dtype) == 0) return fail(HSM_ERR_ARG, "unknown prior dtype %d", prior_dtype);
+    if (!reinit_messages && m->frames != 0 && n_frames != m->frames)
+        return fail(HSM_ERR_ARG, "warm start with %d frames but the state holds %d", n_frames, m->frames);
+    HSM_TRY(ensure_ready(m));
+    const size_t n = (size_t)n_frames * m->H * m->W;
+    m->frames = n_frames;
+    HSM_TRY(load_image(m, m->L, left, image_dtype, 0, n, on_device));
+    HSM_TRY(load_image(m, m->R, right, image_dtype, 1, n, on_device));
+    m->have_prior = (prior != nullptr && prior_mode != HSM_PRIOR_NONE);
+    m->blend.mode = m->have_prior ? prior_mode : kPriorNone;
+    m->blend.keep32 = keep_f32;
+    m->blend.keep64 = keep_f64;
+    if (m->have_prior) HSM_TRY(load_prior(m, prior, prior_dtype, n, on_device));
+    if (reinit_messages) {                                   // mrf.py:43-48
+        const size_t bytes = (size_t)n_frames * m->H * m->W * m->Dp * sizeof(float);
+        CUDA_TRY(cudaMemsetAsync(m->S, 0, bytes, m->stream));
+        CUDA_TRY(cudaMemsetAsync(m->Wm[m->cur], 0, bytes, m->stream));
+        CUDA_TRY(cudaMemsetAsync(m->Nm[m->cur], 0, bytes, m->stream));
+        CUDA_TRY(cudaMemsetAsync(m->Em[m->cur], 0, bytes, m->stream));
+        m->s_valid = true;
+    }
+    m->have_fields = true;
+    m->dt_valid = false;
+    // a pageable host buffer may be reused by the caller as soon as we return
+    if (!on_device) CUDA_TRY(cudaStreamSynchronize(m->stream));
+    return HSM_OK;
+}
+
+int hsm_iterate(hsm_matcher *m, int n_iter, int finalize)
+{
+    if (!m) return fail(HSM_ERR_ARG, "null matcher");
+    if (n_iter < 0) return fail(HSM_ERR_ARG, "n_iter %d < 0", n_iter);
+    if (!m->have_fields) return fail(HSM_ERR_STATE, "hsm_iterate before hsm_init_fields");
+    if (n_iter == 0) return HSM_OK;
+    HSM_TRY(ensure_ready(m));
+    if (m->algorithm == 0 || m->data_term == 0) HSM_TRY(ensure_data_plane(m));
+    std::pair<cudaEvent_t, cudaEvent_t> ev;
+    if (m->pending.size() >= 512) HSM_TRY(resolve_events(m));
+    if (!m->pool.empty()) { ev = m->pool.back(); m->pool.pop_back(); }
+    else { CUDA_TRY(cudaEventCreate(&ev.first)); CUDA_TRY(cudaEventCreate(&ev.second)); }
+    CUDA_TRY(cudaEventRecord(ev.first, m->stream));
+    for (int it = 0; it < n_iter; ++it) {
+        if (m->algorithm == 0) {
+            HSM_TRY(launch_directional(m));
+        } else {
+            const bool store_s = finalize && (it == n_iter - 1);
+            HSM_DISPATCH(m->cfg, { HSM_TRY((launch_fused<LPP, VPL, NT>(m, store_s))); });
+        }
+    }
+    CUDA_TRY(cudaEventRecord(ev.second, m->stream));
+    m->pending.push_back(ev);
+    m->stats.iterations += (uint64_t)n_iter;
+    m->s_valid = (m->algorithm == 0) || finalize;
+    return HSM_OK;
+}
+
+int hsm_readout(hsm_matcher *m, int64_t *labels, int on_device, int async)
+{
+    if (!m) return fail(HSM_ERR_ARG, "null matcher");
+    if (!labels) return fail(HSM_ERR_ARG, "null labels pointer");
+    if (m->frames == 0) return fail(HSM_ERR_STATE, "hsm_readout before hsm_init_fields");
+    if (!m->s_valid) return fail(HSM_ERR_STATE, "south plane is stale: last hsm_iterate was not finalized");
+    HSM_TRY(ensure_ready(m));
+    const Geo g = geometry(m);
+    const bool dt_load = m->dt_valid || !m->have_fields;
+    if (dt_load) HSM_TRY(ensure_data_plane(m));
+    long long *dst = on_device ? (long long *)labels : m->labels;
+    const int *prior = m->have_prior ? m->P : nullptr;
+    HSM_DISPATCH(m->cfg, {
+        (void)NT;
+        const int grid = pixel_grid(m, LPP);
+        if (dt_load)
+            k_readout<LPP, VPL, true><<<grid, 256, 0, m->stream>>>(g, m->frames, m->S, m->Wm[m->cur], m->Nm[m->cur],
+                                                                   m->Em[m->cur], m->Dt, m->L, m->R, prior,
+                                                                   m->blend, dst, nullptr);
+        else
+            k_readout<LPP, VPL, false><<<grid, 256, 0, m->stream>>>(g, m->frames, m->S, m->Wm[m->cur], m->Nm[m->cur],
+                                                                    m->Em[m->cur], m->Dt, m->L, m->R, prior,
+                                                                    m->blend, dst, nullptr);
+    });
+    HSM_TRY(check_launch(m, "k_readout"));
+    if (!on_device) {
+        const size_t bytes = (size_t)m->frames * m->H * m->W * sizeof(long long);
+        CUDA_TRY(cudaMemcpyAsync(labels, m->labels, bytes, cudaMemcpyDeviceToHost, m->stream));
+    }
+    if (!async) CUDA_TRY(cudaStreamSynchronize(m->stream));
+    return HSM_OK;
+}
+
+int hsm_lbp(hsm_matcher *m, int n_frames, const void *left, const void *right, int image_dtype, const void *prior,
+            int prior_dtype, int prior_mode, float keep_f32, double keep_f64, int n_iter, int64_t *labels,
+            int on_device, int async)
+{
+    HSM_TRY(hsm_init_fields(m, n_frames, left, right, image_dtype, prior, prior_dtype, prior_mode, keep_f32,
+                            keep_f64, 1, on_device));
+    HSM_TRY(hsm_iterate(m, n_iter, 1));
+    return hsm_readout(m, labels, on_device, async);
+}
+
+int hsm_sync(hsm_matcher *m)
+{
+    if (!m) return fail(HSM_ERR_ARG, "null matcher");
+    if (!m->ready) return HSM_OK;
+    CUDA_TRY(cudaSetDevice(m->device));
+    CUDA_TRY(cudaStreamSynchronize(m->stream));
+    return HSM_OK;
+}
+
+int hsm_get_plane(hsm_matcher *m, int frame, int which, float *out)
+{
+    HSM_TRY(check_frame(m, frame, which, 5));
+    if (!out) return fail(HSM_ERR_ARG, "null output");
+    HSM_TRY(ensure_ready(m));
+    if (which == 0 && !m->s_valid) return fail(HSM_ERR_STATE, "south plane is stale: last hsm_iterate was not finalized");
+    if (which == 4) HSM_TRY(ensure_data_plane(m));
+    const float *src = plane_ptr(m, which) + (size_t)frame * m->H * m->W * m->Dp;
+    CUDA_TRY(cudaMemcpy2DAsync(out, (size_t)m->D * 4, src, (size_t)m->Dp * 4, (size_t)m->D * 4,
+                               (size_t)m->H * m->W, cudaMemcpyDeviceToHost, m->stream));
+    CUDA_TRY(cudaStreamSynchronize(m->stream));
+    return HSM_OK;
+}
+
+int hsm_set_plane(hsm_matcher *m, int frame, int which, const float *in)
+{
+    HSM_TRY(check_frame(m, frame, which, 4));
+    if (!in) return fail(HSM_ERR_ARG, "null input");
+    HSM_TRY(ensure_ready(m));
+    float *dst = plane_ptr(m, which) + (size_t)frame * m->H * m->W * m->Dp;
+    CUDA_TRY(cudaMemcpy2DAsync(dst, (size_t)m->Dp * 4, in, (size_t)m->D * 4, (size_t)m->D * 4,
+                               (size_t)m->H * m->W, cudaMemcpyHostToDevice, m->stream));
+    CUDA_TRY(cudaStreamSynchronize(m->stream));
+    if (m->frames <= frame) m->frames = frame + 1;
+    return HSM_OK;
+}
+
+int hsm_get_energy(hsm_matcher *m, int frame, float *out)
+{
+    HSM_TRY(check_frame(m, frame, 0, 1));
+    if (!out) return fail(HSM_ERR_ARG, "null output");
+    if (m->frames == 0) return fail(HSM_ERR_STATE, "hsm_get_energy before hsm_init_fields");
+    if (!m->s_valid) return fail(HSM_ERR_STATE, "south plane is stale: last hsm_iterate was not finalized");
+    HSM_TRY(ensure_ready(m));
+    HSM_TRY(ensure_data_plane(m));
+    // the staging area doubles as scratch for one frame's energy (needs H*W*Dp*4 <= 3*cap*H*W*8 -> Dp <= 6*cap)
+    float *scratch = nullptr;
+    const size_t need = (size_t)m->frames * m->H * m->W * m->Dp * sizeof(float);
+    CUDA_TRY(cudaMallocAsync((void **)&scratch, need, m->stream));
+    const Geo g = geometry(m);
+    const int *prior = m->have_prior ? m->P : nullptr;
+    HSM_DISPATCH(m->cfg, {
+        (void)NT;
+        k_readout<LPP, VPL, true><<<pixel_grid(m, LPP), 256, 0, m->stream>>>(
+            g, m->frames, m->S, m->Wm[m->cur], m->Nm[m->cur], m->Em[m->cur], m->Dt, m->L, m->R, prior, m->blend,
+            m->labels, scratch);
+    });
+    HSM_TRY(check_launch(m, "k_readout(energy)"));
+    const float *src = scratch + (size_t)frame * m->H * m->W * m->Dp;
+    CUDA_TRY(cudaMemcpy2DAsync(out, (size_t)m->D * 4, src, (size_t)m->Dp * 4, (size_t)m->D * 4,
+                               (size_t)m->H * m->W, cudaMemcpyDeviceToHost, m->stream));
+    CUDA_TRY(cudaFreeAsync(scratch, m->stream));
+    CUDA_TRY(cudaStreamSynchronize(m->stream));
+    return HSM_OK;
+}
+
+int hsm_halo_floats(hsm_matcher *m, size_t *count)
+{
+    if (!m || !count) return fail(HSM_ERR_ARG, "null argument");
+    *count = (size_t)3 * m->W * m->Dp;
+    return HSM_OK;
+}
+
+int hsm_halo_pack(hsm_matcher *m, float *top, float *bottom)
+{
+    if (!m) return fail(HSM_ERR_ARG, "null matcher");
+    if (m->cap != 1) return fail(HSM_ERR_ARG, "row-band mode needs capacity 1");
+    HSM_TRY(ensure_ready(m));
+    const size_t row = (size_t)m->W * m->Dp;
+    const float *planes[3] = {m->Wm[m->cur], m->Nm[m->cur], m->Em[m->cur]};
+    for (int i = 0; i < 3; ++i) {
+        if (top)
+            CUDA_TRY(cudaMemcpyAsync(top + i * row, planes[i] + (size_t)m->olo * row, row * 4,
+                                     cudaMemcpyDeviceToDevice, m->stream));
+        if (bottom)
+            CUDA_TRY(cudaMemcpyAsync(bottom + i * row, planes[i] + (size_t)m->ohi * row, row * 4,
+                                     cudaMemcpyDeviceToDevice, m->stream));
+    }
+    return HSM_OK;
+}
+
+int hsm_halo_unpack(hsm_matcher *m, const float *from_above, const float *from_below)
+{
+    if (!m) return fail(HSM_ERR_ARG, "null matcher");
+    if (m->cap != 1) return fail(HSM_ERR_ARG, "row-band mode needs capacity 1");
+    if (from_above && m->olo < 1) return fail(HSM_ERR_ARG, "no ghost row above row %d", m->olo);
+    if (from_below && m->ohi + 1 >= m->H) return fail(HSM_ERR_ARG, "no ghost row below row %d", m->ohi);
+    HSM_TRY(ensure_ready(m));
+    const size_t row = (size_t)m->W * m->Dp;
+    float *planes[3] = {m->Wm[m->cur], m->Nm[m->cur], m->Em[m->cur]};
+    for (int i = 0; i < 3; ++i) {
+        if (from_above)
+            CUDA_TRY(cudaMemcpyAsync(planes[i] + (size_t)(m->olo - 1) * row, from_above + i * row, row * 4,
+                                     cudaMemcpyDeviceToDevice, m->stream));
+        if (from_below)
+            CUDA_TRY(cudaMemcpyAsync(planes[i] + (size_t)(m->ohi + 1) * row, from_below + i * row, row * 4,
+                                     cudaMemcpyDeviceToDevice, m->stream));
+    }
+    return HSM_OK;
+}
+
+int hsm_get_stats(hsm_matcher *m, hsm_stats *out)
+{
+    if (!m || !out) return fail(HSM_ERR_ARG, "null argument");
+    if (m->ready) {
+        CUDA_TRY(cudaSetDevice(m->device));
+        HSM_TRY(resolve_events(m));
+    }
+    *out = m->stats;
+    return HSM_OK;
+}
+
+int hsm_reset_stats(hsm_matcher *m)
+{
+    if (!m) return fail(HSM_ERR_ARG, "null matcher");
+    if (m->ready) {
+        CUDA_TRY(cudaSetDevice(m->device));
+        HSM_TRY(resolve_events(m));
+    }
+    const uint64_t bytes = m->stats.device_bytes;
+    m->stats = hsm_stats{};
+    m->stats.device_bytes = bytes;
+    return HSM_OK;
+}
+
+int hsm_selftest_division(const float *a4, const float *b, size_t n, unsigned long long *mismatches)
+{
+    if (!a4 || !b || !mismatches) return fail(HSM_ERR_ARG, "null argument");
+    float4 *da = nullptr;
+    float *db = nullptr;
+    unsigned long long *dm = nullptr;
+    CUDA_TRY(cudaMalloc((void **)&da, n * sizeof(float4)));
+    CUDA_TRY(cudaMalloc((void **)&db, n * sizeof(float)));
+    CUDA_TRY(cudaMalloc((void **)&dm, sizeof(unsigned long long)));
+    CUDA_TRY(cudaMemcpy(da, a4, n * sizeof(float4), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(db, b, n * sizeof(float), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemset(dm, 0, sizeof(unsigned long long)));
+    k_division_selftest<<<148 * 8, 256>>>(da, db, dm, n);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpy(mismatches, dm, sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    cudaFree(da); cudaFree(db); cudaFree(dm);
+    return HSM_OK;
+}
+
+int hsm_host_alloc(size_t bytes, void **out)
+{
+    if (!out) return fail(HSM_ERR_ARG, "null output");
+    CUDA_TRY(cudaHostAlloc(out, bytes, cudaHostAllocDefault));
+    return HSM_OK;
+}
+
+int hsm_host_free(void *p)
+{
+    if (p) CUDA_TRY(cudaFreeHost(p));
+    return HSM_OK;
+}
+
+}  // extern "C"

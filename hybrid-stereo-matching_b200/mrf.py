@@ -1,0 +1,225 @@
+"""``StereoMRF`` -- drop-in for ``stereovis.framed.algorithms.mrf.StereoMRF``.
+
+Same constructor, methods, defaults and return types as the reference class
+(reference mrf.py:8-167); the numpy arithmetic is replaced by the sm_100a CUDA
+kernels behind the C ABI of ``include/hsm.h``.  There is no CPU fallback.
+
+Differences that are deliberate and invisible to the reference's callers:
+  * state lives on the GPU; ``_message_field`` / ``_belief_field`` are read-back
+    properties that return the reference's ``(D, H, W)`` float32 layout;
+  * no CUDA call happens before the first compute call, because the reference's
+    online mode constructs the matcher in the parent and calls ``lbp`` in a
+    ``fork()``ed child (hybrid_stereo.py:107-111 -> online_processing.py:148);
+  * extra, optional surface: ``capacity`` (frames per launch) and ``lbp_batch``.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _capi
+
+_IMAGE_CODES = {np.dtype(np.float32): _capi.F32, np.dtype(np.float64): _capi.F64}
+_PRIOR_CODES = {np.dtype(np.float32): _capi.F32, np.dtype(np.float64): _capi.F64,
+                np.dtype(np.int32): _capi.I32, np.dtype(np.int64): _capi.I64}
+
+
+def _as_image(array):
+    """C-contiguous float32/float64 view or copy; other dtypes are cast like
+    ``astype('float32')`` (mrf.py:41-42).  Returns (array, dtype code)."""
+    array = np.asarray(array)
+    if array.dtype not in _IMAGE_CODES:
+        array = array.astype("float32")
+    array = np.ascontiguousarray(array)
+    return array, _IMAGE_CODES[array.dtype]
+
+
+def _as_prior(array):
+    array = np.asarray(array)
+    if array.dtype not in _PRIOR_CODES:
+        array = array.astype(np.float64 if array.dtype.kind == "f" else np.int64)
+    array = np.ascontiguousarray(array)
+    return array, _PRIOR_CODES[array.dtype]
+
+
+def _blend(prior, prior_trust_factor, prior_influence_mode):
+    """(mode, keep_f32, keep_f64) for ``(1 - prior_trust_factor) * data_diff`` (mrf.py:58-66).
+
+    A Python float factor is a weak scalar: the product is float32, i.e.
+    ``float32(1 - tau) * diff``.  A numpy float64 scalar makes numpy compute the
+    product in float64 before the store into the float32 plane.
+    """
+    if prior is None:
+        return _capi.PRIOR_NONE, 0.0, 0.0
+    if prior_influence_mode == "adaptive":
+        return _capi.PRIOR_ADAPTIVE, 0.0, 0.0
+    keep = 1 - prior_trust_factor
+    if isinstance(keep, np.floating) and keep.dtype == np.float64:
+        return _capi.PRIOR_CONST_F64, 0.0, float(keep)
+    return _capi.PRIOR_CONST, float(np.float32(keep)), 0.0
+
+
+class StereoMRF(object):
+    """Markov random field stereo matcher with the reference's message-passing schedule."""
+
+    def __init__(self, dim, n_levels, capacity=1, device=0):
+        dim = tuple(int(d) for d in dim)
+        self.n_levels = n_levels
+        self.dimension = (n_levels,) + dim                              # mrf.py:13-14
+        self.capacity = int(capacity)
+        self.device = int(device)
+        self._rows, self._cols = dim
+        self._handle = ctypes.c_void_p()
+        _capi.check(_capi.lib().hsm_create(self._rows, self._cols, int(n_levels), self.capacity,
+                                           self.device, ctypes.byref(self._handle)))
+        self._frames = 0
+        self._batched = False
+
+    def __del__(self):
+        handle = getattr(self, "_handle", None)
+        if handle is not None and handle.value:
+            try:
+                _capi.lib().hsm_destroy(handle)
+            except Exception:
+                pass
+            self._handle = None
+
+    # ------------------------------------------------------------------ options
+    def set_option(self, key, value):
+        _capi.check(_capi.lib().hsm_set_option(self._handle, int(key), int(value)))
+
+    def get_option(self, key):
+        out = ctypes.c_int()
+        _capi.check(_capi.lib().hsm_get_option(self._handle, int(key), ctypes.byref(out)))
+        return out.value
+
+    def set_stream(self, cuda_stream):
+        _capi.check(_capi.lib().hsm_set_stream(self._handle, ctypes.c_void_p(int(cuda_stream))))
+
+    def stats(self):
+        out = _capi.Stats()
+        _capi.check(_capi.lib().hsm_get_stats(self._handle, ctypes.byref(out)))
+        return {name: getattr(out, name) for name, _ in _capi.Stats._fields_}
+
+    def reset_stats(self):
+        _capi.check(_capi.lib().hsm_reset_stats(self._handle))
+
+    def synchronize(self):
+        _capi.check(_capi.lib().hsm_sync(self._handle))
+
+    # ------------------------------------------------------------- reference API
+    def _check_pair(self, image_left, image_right, prior, batched):
+        image_left, image_right = np.asarray(image_left), np.asarray(image_right)
+        assert image_left.shape == image_right.shape                     # mrf.py:40
+        frame_shape = image_left.shape[1:] if batched else image_left.shape
+        if frame_shape != (self._rows, self._cols):
+            # the reference fails with a numpy broadcasting ValueError here (mrf.py:70)
+            raise ValueError("could not broadcast input array from shape %r into shape %r"
+                             % (frame_shape, (self._rows, self._cols)))
+        if prior is not None:
+            prior = np.asarray(prior)
+            assert image_right.shape == prior.shape                      # mrf.py:53
+        return image_left, image_right, prior
+
+    def _init_fields(self, image_left, image_right, prior=None, prior_trust_factor=1.0,
+                     prior_influence_mode="adaptive", reinit_messages=True, _batched=False):
+        """Cost volume + optional prior blend + optional message reset (mrf.py:21-71)."""
+        image_left, image_right, prior = self._check_pair(image_left, image_right, prior, _batched)
+        n_frames = image_left.shape[0] if _batched else 1
+        left, code = _as_image(image_left)
+        right, code_r = _as_image(image_right)
+        if code_r != code:
+            left, right = left.astype("float32"), right.astype("float32")
+            code = _capi.F32
+        mode, keep32, keep64 = _blend(prior, prior_trust_factor, prior_influence_mode)
+        prior_ptr, prior_code = None, _capi.F32
+        if prior is not None:
+            prior, prior_code = _as_prior(prior)
+            prior_ptr = prior.ctypes.data_as(ctypes.c_void_p)
+        _capi.check(_capi.lib().hsm_init_fields(
+            self._handle, n_frames, left.ctypes.data_as(ctypes.c_void_p),
+            right.ctypes.data_as(ctypes.c_void_p), code, prior_ptr, prior_code, mode,
+            keep32, keep64, 1 if reinit_messages else 0, 0))
+        self._frames, self._batched = n_frames, _batched
+
+    def _update_message_fields(self):
+        """One iteration: south, west, north, east sweeps (mrf.py:73-94)."""
+        _capi.check(_capi.lib().hsm_iterate(self._handle, 1, 1))
+
+    def loop_belief(self, image_left, image_right, prior=None, prior_trust_factor=1.0,
+                    prior_influence_mode="const", n_iter=10, reinit_messages=True):
+        """Initialise the fields and run ``n_iter`` iterations (mrf.py:106-134)."""
+        self._init_fields(image_left, image_right, prior, prior_trust_factor,
+                          prior_influence_mode, reinit_messages=reinit_messages)
+        _capi.check(_capi.lib().hsm_iterate(self._handle, int(n_iter), 1))
+
+    def _readout(self):
+        if self._frames == 0:
+            # never initialised: all planes are zero, argmin of zeros is 0 (mrf.py:103-104)
+            return np.zeros((self._rows, self._cols), dtype=np.int64)
+        labels = np.empty((self._frames, self._rows, self._cols), dtype=np.int64)
+        _capi.check(_capi.lib().hsm_readout(self._handle, labels.ctypes.data_as(ctypes.c_void_p), 0, 0))
+        return labels if self._batched else labels[0]
+
+    def _update_belief_field(self):
+        self._belief_field_cache = self._readout()
+
+    def get_map_belief(self):
+        """MAP disparity map, int64 ``(H, W)`` like ``np.argmin`` (mrf.py:136-144)."""
+        self._update_belief_field()
+        return self._belief_field_cache
+
+    def lbp(self, image_left, image_right, prior=None, prior_trust_factor=0.5,
+            prior_influence_mode="const", n_iter=10):
+        """``loop_belief`` (always re-initialising) + ``get_map_belief`` (mrf.py:146-167)."""
+        self.loop_belief(image_left=image_left, image_right=image_right, prior=prior,
+                         prior_trust_factor=prior_trust_factor,
+                         prior_influence_mode=prior_influence_mode, n_iter=n_iter,
+                         reinit_messages=True)
+        return self.get_map_belief()
+
+    # ----------------------------------------------------------------- extensions
+    def lbp_batch(self, images_left, images_right, priors=None, prior_trust_factor=0.5,
+                  prior_influence_mode="const", n_iter=10):
+        """``lbp`` over a stack of independent frame pairs ``(N, H, W)`` -> ``(N, H, W)`` int64.
+
+        Frames are processed ``capacity`` at a time; each frame's result equals
+        what ``lbp`` returns for it alone (every call re-initialises, mrf.py:165).
+        """
+        images_left, images_right = np.asarray(images_left), np.asarray(images_right)
+        priors = None if priors is None else np.asarray(priors)
+        assert images_left.ndim == 3 and images_left.shape == images_right.shape
+        n_total = images_left.shape[0]
+        out = np.empty((n_total, self._rows, self._cols), dtype=np.int64)
+        for start in range(0, n_total, self.capacity):
+            stop = min(start + self.capacity, n_total)
+            self._init_fields(images_left[start:stop], images_right[start:stop],
+                              None if priors is None else priors[start:stop],
+                              prior_trust_factor, prior_influence_mode, True, _batched=True)
+            _capi.check(_capi.lib().hsm_iterate(self._handle, int(n_iter), 1))
+            out[start:stop] = self._readout()
+        return out
+
+    # ------------------------------------------------------- read-back accessors
+    def _plane(self, which, frame=0):
+        out = np.empty((self._rows, self._cols, self.n_levels), dtype=np.float32)
+        _capi.check(_capi.lib().hsm_get_plane(self._handle, int(frame), int(which),
+                                              out.ctypes.data_as(ctypes.c_void_p)))
+        return np.ascontiguousarray(out.transpose(2, 0, 1))
+
+    def message_field(self, frame=0):
+        """The reference's ``_message_field`` dict for one frame: name -> (D, H, W) float32."""
+        return {name: self._plane(index, frame) for index, name in enumerate(_capi.PLANES)}
+
+    @property
+    def _message_field(self):
+        return self.message_field(0)
+
+    @property
+    def _belief_field(self):
+        return self._belief_field_cache
+
+    def energy_field(self, frame=0):
+        """Energy of mrf.py:103 for one frame, (D, H, W) float32."""
+        out = np.empty((self._rows, self._cols, self.n_levels), dtype=np.float32)
+        _capi.check(_capi.lib().hsm_get_energy(self._handle, int(frame), out.ctypes.data_as(ctypes.c_void_p)))
+        return np.ascontiguousarray(out.transpose(2, 0, 1))

@@ -1,0 +1,173 @@
+/*
+ * hsm.h -- C ABI of the B200-native frame-based MRF stereo matcher.
+ *
+ * This is the drop-in boundary for ONE hot path of gdikov/hybrid-stereo-matching:
+ * stereovis/framed/algorithms/mrf.py, class StereoMRF (reference mrf.py:8-167).
+ * Every entry point names the reference interface it replaces.  Signatures use
+ * plain pointers and sizes only (no torch / numpy types); the Python class
+ * `StereoMRF` in hybrid-stereo-matching_b200/mrf.py binds them with ctypes and
+ * keeps the reference's method surface.  INTEGRATION.md shows the binding a
+ * maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every function returns HSM_OK (0) or an HSM_ERR_* code; the message is
+ *     available from hsm_last_error() (thread-local);
+ *   - images are row-major (rows x cols) arrays, frames stacked outermost;
+ *   - message/data planes live on the device as frames x rows x cols x Dp float32,
+ *     disparity INNERMOST, Dp = n_levels rounded up to a multiple of 4 (the
+ *     reference keeps (D, H, W); hsm_get_plane returns rows x cols x D and the
+ *     Python layer transposes for `_message_field`);
+ *   - plane indices follow the reference's dict order (mrf.py:15-19):
+ *     0 south, 1 west, 2 north, 3 east, 4 data;
+ *   - no CUDA call is made before the first compute call (hsm_create only
+ *     records the geometry), because the reference constructs the matcher in a
+ *     parent process and runs it in a fork()ed child (hybrid_stereo.py:107-111,
+ *     online_processing.py:148).
+ *   - one matcher = one CUDA stream; calls on one matcher are not thread-safe.
+ */
+#ifndef HSM_H_
+#define HSM_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HSM_OK 0
+#define HSM_ERR_ARG 1    /* bad argument / shape contract violated           */
+#define HSM_ERR_CUDA 2   /* CUDA runtime error (Python raises RuntimeError)   */
+#define HSM_ERR_STATE 3  /* call sequence error (e.g. readout of a stale S)   */
+
+/* element types of caller arrays */
+#define HSM_F32 0
+#define HSM_F64 1
+#define HSM_I32 2
+#define HSM_I64 3
+
+/* prior blending, reference mrf.py:52-67 */
+#define HSM_PRIOR_NONE 0      /* prior is ignored / absent                                    */
+#define HSM_PRIOR_CONST 1     /* Dt = keep_f32 * diff where prior == l   (keep = (float)(1 - tau)) */
+#define HSM_PRIOR_ADAPTIVE 2  /* Dt = (1 - diff) * diff where prior == l                       */
+#define HSM_PRIOR_CONST_F64 3 /* Dt = (float)(keep_f64 * (double)diff): tau was a numpy float64 scalar */
+
+/* hsm_set_option keys */
+#define HSM_OPT_ALGORITHM 0   /* 0 = one kernel per direction (T80), 1 = fused iteration (default)  */
+#define HSM_OPT_BAND_ROWS 1   /* rows per CTA band in the fused kernel; 0 = heuristic                */
+#define HSM_OPT_DATA_TERM 2   /* 0 = read the data plane (T28), 1 = recompute it in-kernel (T24, default) */
+#define HSM_OPT_VALID_LO 3    /* row-band mode: first/last local row that is inside the image ...    */
+#define HSM_OPT_VALID_HI 4
+#define HSM_OPT_OUT_LO 5      /* ... and first/last local row this matcher owns (computes)           */
+#define HSM_OPT_OUT_HI 6
+#define HSM_OPT_FAST_DIV 7    /* 1 = shared-reciprocal correctly rounded division (default), 0 = div.rn.f32 */
+
+typedef struct hsm_matcher hsm_matcher;
+
+typedef struct hsm_stats {
+    uint64_t kernel_launches;      /* kernels of this library launched by this matcher        */
+    uint64_t iteration_launches;   /* message-kernel launches (4 per iteration if algorithm 0) */
+    uint64_t iterations;           /* BP iterations executed                                   */
+    double iteration_ms;           /* device time of all hsm_iterate loops (CUDA events)       */
+    uint64_t device_bytes;         /* device memory owned by the matcher                       */
+} hsm_stats;
+
+int hsm_version(void);
+const char *hsm_last_error(void);
+/* number of CUDA devices visible; fails with HSM_ERR_CUDA when there is no usable GPU */
+int hsm_device_count(int *count);
+
+/*
+ * Replaces StereoMRF.__init__ (mrf.py:12-19): a matcher for `capacity` frames of
+ * rows x cols pixels and n_levels disparities.  Requires n_levels <= cols + 1 (the
+ * reference's slicing fails beyond that) and n_levels <= 512.  No CUDA call.
+ */
+int hsm_create(int rows, int cols, int n_levels, int capacity, int device, hsm_matcher **out);
+int hsm_destroy(hsm_matcher *m);
+
+/* Use the caller's CUDA stream (a cudaStream_t passed as void*) instead of the matcher's own. */
+int hsm_set_stream(hsm_matcher *m, void *cuda_stream);
+int hsm_set_option(hsm_matcher *m, int key, int value);
+int hsm_get_option(hsm_matcher *m, int key, int *value);
+/* Bytes of device memory the matcher needs (allocated on first use). */
+int hsm_device_bytes(int rows, int cols, int n_levels, int capacity, size_t *bytes);
+
+/*
+ * Replaces StereoMRF._init_fields (mrf.py:21-71) for n_frames <= capacity frames:
+ * casts the images to float32 (mrf.py:41-42), zeroes the four message planes if
+ * reinit_messages (mrf.py:43-48) and defines the data term (+ prior blend).
+ * left/right: n_frames x rows x cols of image_dtype (HSM_F32 / HSM_F64).
+ * prior: NULL or n_frames x rows x cols of prior_dtype (any HSM_* type); an entry
+ * matches level l iff it equals l exactly (mrf.py:57); -1 / NaN match nothing.
+ * on_device != 0: the pointers are device pointers on the matcher's device.
+ * The inputs are snapshotted (the online prior is a live shared buffer,
+ * online_processing.py:121).
+ */
+int hsm_init_fields(hsm_matcher *m, int n_frames, const void *left, const void *right,
+                    int image_dtype, const void *prior, int prior_dtype, int prior_mode,
+                    float keep_f32, double keep_f64, int reinit_messages, int on_device);
+
+/*
+ * Replaces the loop over StereoMRF._update_message_fields (mrf.py:73-94, 130-133).
+ * finalize != 0 makes the last iteration also store the south plane (it is a
+ * transient inside a fused iteration); readout needs a finalized state.
+ */
+int hsm_iterate(hsm_matcher *m, int n_iter, int finalize);
+
+/*
+ * Replaces StereoMRF._update_belief_field / get_map_belief (mrf.py:96-104, 136-144):
+ * labels[f, y, x] = first argmin over l of (((S + W) + N) + E) + Dt, int64 like
+ * np.argmin.  labels: n_frames x rows x cols int64, host (or device if on_device).
+ * async != 0: do not wait for the copy (call hsm_sync before reading a host buffer;
+ * the buffer should be pinned, see hsm_host_alloc).
+ */
+int hsm_readout(hsm_matcher *m, int64_t *labels, int on_device, int async);
+
+/* Replaces StereoMRF.lbp (mrf.py:146-167): init (reinit) + n_iter iterations + readout. */
+int hsm_lbp(hsm_matcher *m, int n_frames, const void *left, const void *right, int image_dtype,
+            const void *prior, int prior_dtype, int prior_mode, float keep_f32, double keep_f64,
+            int n_iter, int64_t *labels, int on_device, int async);
+
+int hsm_sync(hsm_matcher *m);
+
+/*
+ * Read-back of `StereoMRF._message_field[...]` (mrf.py:15-19) for one frame:
+ * out is rows x cols x n_levels float32 on the host (disparity innermost).
+ */
+int hsm_get_plane(hsm_matcher *m, int frame, int which, float *out);
+/* Energy field of mrf.py:103, same layout as hsm_get_plane. */
+int hsm_get_energy(hsm_matcher *m, int frame, float *out);
+/* Overwrite one plane of one frame from the host (tests, warm start from saved state). */
+int hsm_set_plane(hsm_matcher *m, int frame, int which, const float *in);
+
+/*
+ * Row-band mode (one large frame split across GPUs).  The
+ * matcher holds local rows [0, rows) of which [out_lo, out_hi] are owned and the
+ * rest are ghost rows.  After each iteration the owned boundary rows of the three
+ * planes that cross an iteration (west, north, east) are exchanged:
+ *   pack:   top    <- row out_lo of (W, N, E), bottom <- row out_hi   (3 x cols x Dp floats each)
+ *   unpack: row out_lo - 1 <- from_above, row out_hi + 1 <- from_below (NULL = skip)
+ * All pointers are device pointers; copies are ordered on the matcher's stream.
+ */
+int hsm_halo_floats(hsm_matcher *m, size_t *count);
+int hsm_halo_pack(hsm_matcher *m, float *top, float *bottom);
+int hsm_halo_unpack(hsm_matcher *m, const float *from_above, const float *from_below);
+
+int hsm_get_stats(hsm_matcher *m, hsm_stats *out);
+int hsm_reset_stats(hsm_matcher *m);
+
+/*
+ * Self-test of the shared-reciprocal division used by the fused kernel: a4 holds n x 4
+ * numerators, b holds n divisors (host arrays); *mismatches = how many of the 4n quotients
+ * differ in bits from div.rn.f32 (must be 0).
+ */
+int hsm_selftest_division(const float *a4, const float *b, size_t n, unsigned long long *mismatches);
+
+/* Pinned host memory for asynchronous transfers. */
+int hsm_host_alloc(size_t bytes, void **out);
+int hsm_host_free(void *p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HSM_H_ */

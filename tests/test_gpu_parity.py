@@ -1,0 +1,161 @@
+"""Parity of the CUDA path (through the C ABI / StereoMRF) against the golden fixtures
+of the real reference and against the CPU oracles.  Bar: planes bit-identical
+(np.array_equal), labels identical.  Runs on the B200 box: pytest -m gpu."""
+import hashlib
+
+import numpy as np
+import pytest
+
+from oracle import cases as C
+from oracle import mrf_c
+
+pytestmark = pytest.mark.gpu
+
+ALL = [(c, True) for c in C.SMALL_CASES] + [(c, False) for c in C.BIG_CASES]
+IDS = [c["name"] for c, _ in ALL]
+# (algorithm, data_term): fused + recomputed data term (default), fused + data plane, one kernel per direction
+VARIANTS = [(1, 1), (1, 0), (0, 0)]
+
+
+def _factory(hsm, algorithm, data_term, band_rows=0, capacity=1):
+    from importlib import import_module
+    capi = import_module("hybrid-stereo-matching_b200._capi")
+
+    def make(dim, levels):
+        m = hsm.StereoMRF(tuple(dim), levels, capacity=capacity)
+        m.set_option(capi.OPT_ALGORITHM, algorithm)
+        m.set_option(capi.OPT_DATA_TERM, data_term)
+        m.set_option(capi.OPT_BAND_ROWS, band_rows)
+        return m
+    return make
+
+
+@pytest.mark.parametrize("variant", VARIANTS, ids=["fused_T24", "fused_T28", "directional_T80"])
+@pytest.mark.parametrize("case,small", ALL, ids=IDS)
+def test_cuda_matches_reference_fixture(hsm, case, small, variant):
+    labels, planes = C.run_case(_factory(hsm, *variant), case)
+    data, meta = C.load_fixture(case)
+    assert labels.dtype == np.int64
+    mism = int((labels != data["labels"]).sum())
+    assert mism == 0, "%d of %d labels differ" % (mism, labels.size)
+    assert hashlib.sha1(labels.astype(np.int32).tobytes()).hexdigest() == meta["labels_sha1"]
+    for name, plane in planes.items():
+        assert plane.dtype == np.float32 and plane.shape == (case["levels"],) + labels.shape
+        if small:
+            want = data["plane_" + name]
+            assert np.array_equal(plane, want, equal_nan=True), \
+                "%s: max abs diff %g" % (name, float(np.nanmax(np.abs(plane - want))))
+        assert C.plane_sha1(plane) == meta["plane_sha1"][name], name
+
+
+@pytest.mark.parametrize("band_rows", [1, 2, 5, 7])
+def test_band_height_does_not_change_results(hsm, band_rows):
+    for case in (C.SMALL_CASES[3], C.SMALL_CASES[12], C.SMALL_CASES[24]):
+        labels, planes = C.run_case(_factory(hsm, 1, 1, band_rows=band_rows), case)
+        data, _ = C.load_fixture(case)
+        assert np.array_equal(labels, data["labels"])
+        for name, plane in planes.items():
+            assert np.array_equal(plane, data["plane_" + name]), (case["name"], name)
+
+
+def test_random_shapes_against_c_oracle(hsm):
+    rng = np.random.default_rng(99)
+    for trial in range(40):
+        rows, cols = int(rng.integers(1, 40)), int(rng.integers(2, 90))
+        levels = int(rng.integers(1, min(cols + 1, 70) + 1))
+        n_iter = int(rng.integers(0, 6))
+        left, right = rng.random((rows, cols)), rng.random((rows, cols))
+        if trial % 5 == 0:
+            left, right = left.astype(np.float32), right.astype(np.float32)
+        prior, kwargs = None, dict(n_iter=n_iter)
+        if trial % 3:
+            prior = rng.integers(-1, levels, size=(rows, cols)).astype(
+                [np.float64, np.int32, np.float32, np.int64][trial % 4])
+            kwargs.update(prior_trust_factor=[0.0, 0.5, 1.0, 10.0, 100.0][trial % 5],
+                          prior_influence_mode=["const", "adaptive"][trial % 2])
+        want_obj = mrf_c.OracleMRFC((rows, cols), levels)
+        want = want_obj.lbp(left, right, prior, **kwargs)
+        for variant in VARIANTS:
+            got_obj = _factory(hsm, *variant)((rows, cols), levels)
+            got = got_obj.lbp(left, right, prior, **kwargs)
+            assert np.array_equal(got, want), (trial, variant, rows, cols, levels)
+            want_planes = want_obj._message_field
+            for name, plane in got_obj._message_field.items():
+                assert np.array_equal(plane, want_planes[name]), (trial, variant, name, rows, cols, levels)
+            assert np.array_equal(got_obj.energy_field(), want_obj.energy()), (trial, variant)
+
+
+def test_float64_scalar_trust_factor(hsm):
+    rng = np.random.default_rng(5)
+    left, right = rng.random((9, 14)), rng.random((9, 14))
+    prior = rng.integers(-1, 6, size=(9, 14)).astype(np.float64)
+    want_obj = mrf_c.OracleMRFC((9, 14), 6)
+    want = want_obj.lbp(left, right, prior, prior_trust_factor=np.float64(0.3), n_iter=2)
+    got_obj = hsm.StereoMRF((9, 14), 6)
+    got = got_obj.lbp(left, right, prior, prior_trust_factor=np.float64(0.3), n_iter=2)
+    assert np.array_equal(got, want)
+    assert np.array_equal(got_obj._message_field["data"], want_obj._message_field["data"])
+
+
+def test_batch_equals_single_frames(hsm):
+    from importlib import import_module
+    synth = import_module("hybrid-stereo-matching_b200.synth")
+    lefts, rights, priors = synth.synthetic_sequence(7, 36, 50, 12, base_seed=3)
+    single = hsm.StereoMRF((36, 50), 12)
+    want = np.stack([single.lbp(lefts[i], rights[i], priors[i], prior_trust_factor=1.0,
+                                prior_influence_mode="adaptive", n_iter=6) for i in range(7)])
+    for capacity in (1, 3, 7, 16):
+        batched = hsm.StereoMRF((36, 50), 12, capacity=capacity)
+        got = batched.lbp_batch(lefts, rights, priors, prior_trust_factor=1.0,
+                                prior_influence_mode="adaptive", n_iter=6)
+        assert got.shape == (7, 36, 50) and got.dtype == np.int64
+        assert np.array_equal(got, want), capacity
+    # planes of an inner frame of the batch
+    batched = hsm.StereoMRF((36, 50), 12, capacity=7)
+    batched.lbp_batch(lefts, rights, priors, prior_trust_factor=1.0, prior_influence_mode="adaptive", n_iter=6)
+    single.lbp(lefts[4], rights[4], priors[4], prior_trust_factor=1.0, prior_influence_mode="adaptive", n_iter=6)
+    for name, plane in single._message_field.items():
+        assert np.array_equal(batched.message_field(4)[name], plane), name
+
+
+def test_iteration_by_iteration_equals_one_call(hsm):
+    """_update_message_fields() n times == loop_belief(n_iter=n) (mrf.py:130-133)."""
+    case = C.SMALL_CASES[0]
+    left, right, _, _ = C.case_inputs(case, 0)
+    a = hsm.StereoMRF(left.shape, case["levels"])
+    a.loop_belief(left, right, n_iter=0)
+    for _ in range(3):
+        a._update_message_fields()
+    data, _ = C.load_fixture(case)
+    assert np.array_equal(a.get_map_belief(), data["labels"])
+    for name, plane in a._message_field.items():
+        assert np.array_equal(plane, data["plane_" + name]), name
+
+
+def test_uninitialised_matcher_reads_zero(hsm):
+    m = hsm.StereoMRF((5, 6), 4)
+    out = m.get_map_belief()
+    assert out.dtype == np.int64 and out.shape == (5, 6) and not out.any()
+
+
+def test_full_size_properties_c1_batch(hsm):
+    """BASELINE C1/C2 size, 50 iterations, batch of 4: size-independent properties --
+    messages normalised to max 1 per pixel (or all-zero border lines), labels in range,
+    left border labelled mostly D-1 (zero-cost columns), batch == single."""
+    from importlib import import_module
+    synth = import_module("hybrid-stereo-matching_b200.synth")
+    D = 32
+    lefts, rights, priors = synth.synthetic_sequence(4, 180, 240, D, base_seed=1234)
+    lefts[0], rights[0], priors[0], _ = C.case_inputs(C.BIG_CASES[2], 0)
+    m = hsm.StereoMRF((180, 240), D, capacity=4)
+    labels = m.lbp_batch(lefts, rights, priors, prior_trust_factor=1.0, prior_influence_mode="adaptive", n_iter=50)
+    assert labels.min() >= 0 and labels.max() < D
+    data, meta = C.load_fixture(C.BIG_CASES[2])          # frame 0 == b03 (seed 1234)
+    assert np.array_equal(labels[0], data["labels"])
+    planes = m.message_field(0)
+    for name in ("south", "west", "north", "east"):
+        assert C.plane_sha1(planes[name]) == meta["plane_sha1"][name], name
+        peak = planes[name].max(axis=0)
+        assert np.all((peak == 1.0) | (peak == 0.0)), name
+    assert not planes["south"][:, 0, :].any() and not planes["north"][:, -1, :].any()
+    assert not planes["west"][:, :, -1].any() and not planes["east"][:, :, 0].any()
