@@ -22,7 +22,7 @@ OK, ERR_ARG, ERR_CUDA, ERR_STATE = 0, 1, 2, 3
 F32, F64, I32, I64 = 0, 1, 2, 3
 PRIOR_NONE, PRIOR_CONST, PRIOR_ADAPTIVE, PRIOR_CONST_F64 = 0, 1, 2, 3
 OPT_ALGORITHM, OPT_BAND_ROWS, OPT_DATA_TERM = 0, 1, 2
-OPT_VALID_LO, OPT_VALID_HI, OPT_OUT_LO, OPT_OUT_HI, OPT_FAST_DIV = 3, 4, 5, 6, 7
+OPT_VALID_LO, OPT_VALID_HI, OPT_OUT_LO, OPT_OUT_HI, OPT_STAGES = 3, 4, 5, 6, 7
 PLANES = ("south", "west", "north", "east", "data")      # reference dict order, mrf.py:15-19
 
 
@@ -69,9 +69,10 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
-    if library_is_stale():
+    override = os.environ.get("HSM_B200_LIB")          # development: try an alternative build
+    if override is None and library_is_stale():
         build_library()
-    handle = ctypes.CDLL(LIB_PATH)
+    handle = ctypes.CDLL(override or LIB_PATH)
     vp, ci, cf, cd, sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_double, ctypes.c_size_t
     sig = {
         "hsm_version": ([], ci),

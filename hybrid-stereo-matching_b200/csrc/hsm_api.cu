@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "kernels.cuh"
+#include "iter_tma.cuh"
 
 using namespace hsm;
 
@@ -111,7 +112,10 @@ struct hsm_matcher {
     bool have_fields = false, have_prior = false, dt_valid = false, s_valid = true;
     Blend blend{kPriorNone, 0.0f, 0.0};
     // options
-    int algorithm = 1, band_rows = 0, data_term = 1;
+    int algorithm = 2, band_rows = 0, data_term = 1, stages = 0;
+    // TMA descriptors of the double-buffered planes (algorithm 2)
+    CUtensorMap tmW[2], tmN[2], tmE[2], tmD;
+    bool maps_valid = false;
     int vlo = 0, vhi = 0, olo = 0, ohi = 0;
     // statistics
     hsm_stats stats{};
@@ -309,6 +313,111 @@ int launch_fused(hsm_matcher *m, bool store_s)
     return HSM_OK;
 }
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int encode_fn(EncodeTiledFn *out)
+{
+    static EncodeTiledFn cached = nullptr;
+    if (!cached) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult query;
+        CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &query));
+        if (!fn || query != cudaDriverEntryPointSuccess)
+            return fail(HSM_ERR_CUDA, "driver does not provide cuTensorMapEncodeTiled");
+        cached = (EncodeTiledFn)fn;
+    }
+    *out = cached;
+    return HSM_OK;
+}
+
+// 4-D map (Dp, cols, valid rows, frames) over one plane; box = one row segment of `px` pixels.
+int make_plane_map(const hsm_matcher *m, CUtensorMap *map, float *plane, int px)
+{
+    EncodeTiledFn encode;
+    HSM_TRY(encode_fn(&encode));
+    const cuuint64_t dims[4] = {(cuuint64_t)m->Dp, (cuuint64_t)m->W, (cuuint64_t)(m->vhi - m->vlo + 1),
+                                (cuuint64_t)m->cap};
+    const cuuint64_t strides[3] = {(cuuint64_t)m->Dp * 4, (cuuint64_t)m->W * m->Dp * 4,
+                                   (cuuint64_t)m->H * m->W * m->Dp * 4};
+    const cuuint32_t box[4] = {(cuuint32_t)m->Dp, (cuuint32_t)px, 1, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    float *base = plane + (size_t)m->vlo * m->W * m->Dp;
+    CUresult rc = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, base, dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS) return fail(HSM_ERR_CUDA, "cuTensorMapEncodeTiled failed with code %d", (int)rc);
+    return HSM_OK;
+}
+
+bool tma_supported(const hsm_matcher *m) { return m->Dp <= 256; }
+
+int ensure_maps(hsm_matcher *m)
+{
+    if (m->maps_valid) return HSM_OK;
+    const int px = m->cfg.nt / m->cfg.lpp;
+    for (int i = 0; i < 2; ++i) {
+        HSM_TRY(make_plane_map(m, &m->tmW[i], m->Wm[i], px));
+        HSM_TRY(make_plane_map(m, &m->tmN[i], m->Nm[i], px));
+        HSM_TRY(make_plane_map(m, &m->tmE[i], m->Em[i], px));
+    }
+    HSM_TRY(make_plane_map(m, &m->tmD, m->Dt, px));
+    m->maps_valid = true;
+    return HSM_OK;
+}
+
+template <int LPP, int VPL, int NT>
+int launch_tma(hsm_matcher *m, bool store_s)
+{
+    HSM_TRY(ensure_maps(m));
+    const Geo g = geometry(m);
+    constexpr int PX = NT / LPP, TX = PX - 2, SLOTS = NT + 2 * LPP;
+    const int strips = (m->W + TX - 1) / TX;
+    IterArgs a;
+    a.Win = m->Wm[m->cur]; a.Nin = m->Nm[m->cur]; a.Ein = m->Em[m->cur];
+    a.Wout = m->Wm[m->cur ^ 1]; a.Nout = m->Nm[m->cur ^ 1]; a.Eout = m->Em[m->cur ^ 1];
+    a.Sout = m->S;
+    a.Dt = m->Dt; a.L = m->L; a.R = m->R; a.P = m->have_prior ? m->P : nullptr;
+    a.blend = m->blend;
+    a.olo = m->olo; a.ohi = m->ohi;
+    a.band_rows = choose_band_rows(m, strips);
+    const int bands = (m->ohi - m->olo + 1 + a.band_rows - 1) / a.band_rows;
+    dim3 grid(strips, bands, m->frames);
+    const bool dt_load = (m->data_term == 0);
+    const bool full = (m->D == 4 * LPP * VPL);
+    const size_t stage_bytes = (size_t)(dt_load ? 4 : 3) * PX * m->Dp * 4;
+    const size_t fixed_bytes = (size_t)2 * VPL * SLOTS * 16 + 64;
+    int stages = m->stages;
+    if (stages <= 0) {      // as many stages (2..4) as fit the per-CTA share of shared memory
+        const int target_ctas = (NT == 256) ? 3 : (VPL == 1 ? 2 : 1);
+        const size_t budget = (size_t)227 * 1024 / target_ctas - 1024;
+        stages = 4;
+        while (stages > 2 && fixed_bytes + stages * stage_bytes > budget) --stages;
+    }
+    const size_t smem = fixed_bytes + (size_t)stages * stage_bytes;
+    if (smem > (size_t)227 * 1024) return fail(HSM_ERR_ARG, "fused TMA kernel needs %zu bytes of shared memory", smem);
+    const CUtensorMap &tw = m->tmW[m->cur], &tn = m->tmN[m->cur], &te = m->tmE[m->cur], &td = m->tmD;
+#define HSM_LAUNCH_TMA(S, T, F)                                                                              \
+    do {                                                                                                     \
+        auto kernel = k_iter_tma<LPP, VPL, NT, S, T, F>;                                                     \
+        CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
+        kernel<<<grid, NT, smem, m->stream>>>(tw, tn, te, td, g, a, stages);                                 \
+    } while (0)
+    if (full) {
+        if (store_s) { if (dt_load) HSM_LAUNCH_TMA(true, true, true); else HSM_LAUNCH_TMA(true, false, true); }
+        else { if (dt_load) HSM_LAUNCH_TMA(false, true, true); else HSM_LAUNCH_TMA(false, false, true); }
+    } else {
+        if (store_s) { if (dt_load) HSM_LAUNCH_TMA(true, true, false); else HSM_LAUNCH_TMA(true, false, false); }
+        else { if (dt_load) HSM_LAUNCH_TMA(false, true, false); else HSM_LAUNCH_TMA(false, false, false); }
+    }
+#undef HSM_LAUNCH_TMA
+    HSM_TRY(check_launch(m, "k_iter_tma"));
+    m->stats.iteration_launches++;
+    m->cur ^= 1;
+    return HSM_OK;
+}
+
 int launch_directional(hsm_matcher *m)
 {
     const Geo g = geometry(m);
@@ -422,7 +531,7 @@ int hsm_set_option(hsm_matcher *m, int key, int value)
     if (!m) return fail(HSM_ERR_ARG, "null matcher");
     switch (key) {
         case HSM_OPT_ALGORITHM:
-            if (value != 0 && value != 1) return fail(HSM_ERR_ARG, "algorithm must be 0 or 1");
+            if (value < 0 || value > 2) return fail(HSM_ERR_ARG, "algorithm must be 0, 1 or 2");
             m->algorithm = value; return HSM_OK;
         case HSM_OPT_BAND_ROWS:
             if (value < 0) return fail(HSM_ERR_ARG, "band_rows must be >= 0");
@@ -432,13 +541,15 @@ int hsm_set_option(hsm_matcher *m, int key, int value)
             m->data_term = value; return HSM_OK;
         case HSM_OPT_VALID_LO: case HSM_OPT_VALID_HI: case HSM_OPT_OUT_LO: case HSM_OPT_OUT_HI:
             if (value < 0 || value >= m->H) return fail(HSM_ERR_ARG, "row %d outside [0, %d)", value, m->H);
+            m->maps_valid = false;
             if (key == HSM_OPT_VALID_LO) m->vlo = value;
             else if (key == HSM_OPT_VALID_HI) m->vhi = value;
             else if (key == HSM_OPT_OUT_LO) m->olo = value;
             else m->ohi = value;
             return HSM_OK;
-        case HSM_OPT_FAST_DIV:
-            return HSM_OK;   // reserved; the division is always correctly rounded
+        case HSM_OPT_STAGES:
+            if (value < 0 || value > 8 || value == 1) return fail(HSM_ERR_ARG, "stages must be 0 (auto) or 2..8");
+            m->stages = value; return HSM_OK;
         default: return fail(HSM_ERR_ARG, "unknown option %d", key);
     }
 }
@@ -454,7 +565,7 @@ int hsm_get_option(hsm_matcher *m, int key, int *value)
         case HSM_OPT_VALID_HI: *value = m->vhi; return HSM_OK;
         case HSM_OPT_OUT_LO: *value = m->olo; return HSM_OK;
         case HSM_OPT_OUT_HI: *value = m->ohi; return HSM_OK;
-        case HSM_OPT_FAST_DIV: *value = 0; return HSM_OK;
+        case HSM_OPT_STAGES: *value = m->stages; return HSM_OK;
         default: return fail(HSM_ERR_ARG, "unknown option %d", key);
     }
 }
@@ -526,7 +637,10 @@ int hsm_iterate(hsm_matcher *m, int n_iter, int finalize)
             HSM_TRY(launch_directional(m));
         } else {
             const bool store_s = finalize && (it == n_iter - 1);
-            HSM_DISPATCH(m->cfg, { HSM_TRY((launch_fused<LPP, VPL, NT>(m, store_s))); });
+            if (m->algorithm == 2 && tma_supported(m))
+                HSM_DISPATCH(m->cfg, { HSM_TRY((launch_tma<LPP, VPL, NT>(m, store_s))); });
+            else
+                HSM_DISPATCH(m->cfg, { HSM_TRY((launch_fused<LPP, VPL, NT>(m, store_s))); });
         }
     }
     CUDA_TRY(cudaEventRecord(ev.second, m->stream));

@@ -1,0 +1,226 @@
+// Fused iteration kernel, TMA-fed variant (algorithm 2, the default).
+//
+// Same arithmetic and the same row-streaming structure as k_iter_fused in
+// kernels.cuh (see the derivation there), but the old W / N / E (/ data) rows are
+// brought in by the Tensor Memory Accelerator instead of per-thread LDG:
+//
+//   * each plane is described by a 4-D tensor map (Dp, cols, valid rows, frames);
+//     one cp.async.bulk.tensor per plane moves the CTA's row segment
+//     (PX pixels x Dp floats, contiguous in HBM) into a shared-memory stage;
+//   * out-of-image coordinates (column -1, column >= W, rows outside the valid
+//     range) are ZERO-FILLED by the hardware, which is exactly the "a border line
+//     that receives nothing stays zero" rule of the reference (mrf.py:83-90);
+//   * a ring of `stages` row stages with one mbarrier each keeps several rows in
+//     flight without holding them in registers (the LDG variant needs a second
+//     register set for its one-row prefetch and loses occupancy to it);
+//   * a stage is refilled right after the row's only __syncthreads (every thread
+//     copied its chunk of the stage into registers before that barrier).
+#pragma once
+
+#include <cuda.h>
+
+#include "kernels.cuh"
+
+namespace hsm {
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2,
+                                            int c3)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+
+#ifndef HSM_TMA_MIN_BLOCKS
+#define HSM_TMA_MIN_BLOCKS 3
+#endif
+
+template <int LPP, int VPL, int NT, bool STORE_S, bool DT_LOAD, bool FULL>
+__global__ void __launch_bounds__(NT, (NT == 256 && VPL == 1) ? HSM_TMA_MIN_BLOCKS : 1)
+    k_iter_tma(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmN,
+               const __grid_constant__ CUtensorMap tmE, const __grid_constant__ CUtensorMap tmD, Geo g, IterArgs a,
+               int stages)
+{
+    constexpr int PX = NT / LPP;
+    constexpr int TX = PX - 2;
+    constexpr int SLOTS = NT + 2 * LPP;
+    constexpr int NPL = DT_LOAD ? 4 : 3;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+
+    const int tid = threadIdx.x;
+    const int px = tid / LPP;
+    Lane<LPP, VPL> ln;
+    ln.init(tid % LPP, g.D, g.Dp);
+
+    const unsigned row_floats = (unsigned)PX * (unsigned)g.Dp;          // one plane's row segment
+    float *stage_base = reinterpret_cast<float *>(smem_raw);
+    float4 *exch = reinterpret_cast<float4 *>(smem_raw + (size_t)stages * NPL * row_floats * 4);
+    uint64_t *full = reinterpret_cast<uint64_t *>(exch + 2 * VPL * SLOTS);
+    auto ex = [&](int par, int v, int slot) -> float4 & { return exch[(par * VPL + v) * SLOTS + slot]; };
+
+    const int xs0 = (int)blockIdx.x * TX;
+    const int x = xs0 - 1 + px;
+    const bool in_x = (x >= 0 && x < g.W);
+    const int yb0 = a.olo + (int)blockIdx.y * a.band_rows;
+    const int yb1 = min(yb0 + a.band_rows - 1, a.ohi);
+    const int frame = (int)blockIdx.z;
+    const size_t fplane = (size_t)frame * g.plane_stride;
+    const size_t fimage = (size_t)frame * g.image_stride;
+    const unsigned row_stride = (unsigned)g.W * (unsigned)g.Dp;
+    const int n_rows = yb1 - yb0 + 3;                                    // rows yb0-1 .. yb1+1
+
+    const bool st_w = px >= 2 && (x - 1) < g.W;
+    const bool st_n = in_x && px >= 1 && px <= PX - 2;
+    const bool st_e = px <= PX - 3 && (x + 1) < g.W;
+    const int rd_slot = (x < 0) ? (NT + LPP + ln.c) : (tid + LPP);
+
+    if (tid == 0) {
+        for (int s = 0; s < stages; ++s) mbar_init(&full[s], 1);
+        mbar_fence_init();
+    }
+    if (tid < 2 * LPP) {
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) ex(0, v, NT + tid) = ex(1, v, NT + tid) = zero4();
+    }
+    __syncthreads();
+
+    // producer side (thread 0): one bulk tensor copy per plane into stage s for row index r
+    auto issue = [&](int r, int s) {
+        const int yy = yb0 - 1 + r - g.vlo;            // row coordinate inside the valid-row tensor
+        float *dst = stage_base + (size_t)s * NPL * row_floats;
+        mbar_expect_tx(&full[s], NPL * row_floats * 4u);
+        tma_load_4d(dst, &tmW, &full[s], 0, xs0 - 1, yy, frame);
+        tma_load_4d(dst + row_floats, &tmN, &full[s], 0, xs0 - 1, yy, frame);
+        tma_load_4d(dst + 2 * row_floats, &tmE, &full[s], 0, xs0 - 1, yy, frame);
+        if (DT_LOAD) tma_load_4d(dst + 3 * row_floats, &tmD, &full[s], 0, xs0 - 1, yy, frame);
+    };
+    if (tid == 0) {
+        const int first = n_rows < stages ? n_rows : stages;
+        for (int s = 0; s < first; ++s) issue(s, s);
+    }
+
+    float *Wout = a.Wout + fplane, *Nout = a.Nout + fplane, *Eout = a.Eout + fplane;
+    float *Sout = STORE_S ? a.Sout + fplane : nullptr;
+
+    RowRegs<VPL> cur;
+    Vec<VPL> Scur, Xprev, Dprev;
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) Scur.q[v] = Xprev.q[v] = Dprev.q[v] = cur.d.q[v] = zero4();
+
+    const unsigned lane_f4 = (unsigned)px * (unsigned)(g.Dp / 4) + (unsigned)ln.c;   // float4 index in a row segment
+    int stage = 0;
+    uint32_t phase = 0;
+    // consumer side: wait for row index r, copy this lane's chunks of the stage to registers
+    auto fetch = [&](int y) {
+        mbar_wait(&full[stage], phase);
+        const float4 *sp = reinterpret_cast<const float4 *>(stage_base + (size_t)stage * NPL * row_floats) + lane_f4;
+        const unsigned plane_f4 = row_floats / 4;
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) {
+            if (FULL || ln.active[v]) {
+                cur.w.q[v] = sp[v * LPP];
+                cur.n.q[v] = sp[plane_f4 + v * LPP];
+                cur.e.q[v] = sp[2 * plane_f4 + v * LPP];
+                if (DT_LOAD) cur.d.q[v] = sp[3 * plane_f4 + v * LPP];
+            } else {
+                cur.w.q[v] = cur.n.q[v] = cur.e.q[v] = zero4();
+                if (DT_LOAD) cur.d.q[v] = zero4();
+            }
+        }
+        if (!DT_LOAD) {
+            const bool valid = in_x && y >= g.vlo && y <= g.vhi;
+            data_vec<LPP, VPL>(cur.d, ln, a.L, a.R, a.P, fimage + (size_t)(valid ? y : 0) * g.W, x, g.D, a.blend, valid);
+        }
+    };
+    // after the row's barrier: the stage is free, refill it with row index r + stages
+    auto refill = [&](int r) {
+        if (tid == 0 && r + stages < n_rows) issue(r + stages, stage);
+        if (++stage == stages) { stage = 0; phase ^= 1u; }
+    };
+    auto store_vec = [&](float *plane, int y, int xx, const Vec<VPL> &val) {
+        const unsigned off = (unsigned)y * row_stride + (unsigned)xx * (unsigned)g.Dp + 4u * (unsigned)ln.c;
+#pragma unroll
+        for (int v = 0; v < VPL; ++v)
+            if (FULL || ln.active[v]) st_plain(plane + off + 4 * LPP * v, val.q[v]);
+    };
+
+    // row yb0-1 only contributes S'(yb0)
+    fetch(yb0 - 1);
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) Scur.q[v] = sum4(cur.w.q[v], cur.n.q[v], cur.e.q[v], cur.d.q[v]);
+    normalise<LPP, VPL, FULL>(Scur, ln);
+    if (STORE_S && st_n) store_vec(Sout, yb0, x, Scur);
+    __syncthreads();
+    refill(0);
+
+    int par = 0;
+    for (int y = yb0; y <= yb1 + 1; ++y) {
+        fetch(y);
+        if (y > g.vhi) {
+#pragma unroll
+            for (int v = 0; v < VPL; ++v) Scur.q[v] = zero4();
+        }
+        // S'(y+1, x) = norm(U_S(y, x))
+        Vec<VPL> Snext;
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) Snext.q[v] = sum4(cur.w.q[v], cur.n.q[v], cur.e.q[v], cur.d.q[v]);
+        normalise<LPP, VPL, FULL>(Snext, ln);
+        if (STORE_S && st_n && y + 1 <= yb1) store_vec(Sout, y + 1, x, Snext);
+        // W'(y, x-1) = norm(U_W(y, x))
+        Vec<VPL> t;
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) t.q[v] = sum4(Scur.q[v], cur.n.q[v], cur.e.q[v], cur.d.q[v]);
+        normalise<LPP, VPL, FULL>(t, ln);
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) ex(par, v, tid) = t.q[v];
+        if (st_w && y <= yb1) store_vec(Wout, y, x - 1, t);
+        __syncthreads();
+        refill(y - yb0 + 1);
+        // X = S'(y, x) + W'(y, x)
+        Vec<VPL> X;
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) X.q[v] = add4(Scur.q[v], ex(par, v, rd_slot));
+        // N'(y-1, x) = norm(U_N(y, x))
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) t.q[v] = add4(add4(X.q[v], cur.e.q[v]), cur.d.q[v]);
+        normalise<LPP, VPL, FULL>(t, ln);
+        const bool upper = (y > yb0);
+        if (upper && st_n) store_vec(Nout, y - 1, x, t);
+        // E'(y-1, x+1) = norm(U_E(y-1, x))
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) t.q[v] = add4(add4(Xprev.q[v], t.q[v]), Dprev.q[v]);
+        normalise<LPP, VPL, FULL>(t, ln);
+        if (upper && st_e) store_vec(Eout, y - 1, x + 1, t);
+        Xprev = X;
+        Dprev = cur.d;
+        Scur = Snext;
+        par ^= 1;
+    }
+}
+
+}  // namespace hsm

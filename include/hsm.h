@@ -53,14 +53,15 @@ extern "C" {
 #define HSM_PRIOR_CONST_F64 3 /* Dt = (float)(keep_f64 * (double)diff): tau was a numpy float64 scalar */
 
 /* hsm_set_option keys */
-#define HSM_OPT_ALGORITHM 0   /* 0 = one kernel per direction (T80), 1 = fused iteration (default)  */
+#define HSM_OPT_ALGORITHM 0   /* 0 = one kernel per direction (T80), 1 = fused iteration fed by LDG,
+                                 2 = fused iteration fed by TMA (default; falls back to 1 if n_levels > 256) */
 #define HSM_OPT_BAND_ROWS 1   /* rows per CTA band in the fused kernel; 0 = heuristic                */
 #define HSM_OPT_DATA_TERM 2   /* 0 = read the data plane (T28), 1 = recompute it in-kernel (T24, default) */
 #define HSM_OPT_VALID_LO 3    /* row-band mode: first/last local row that is inside the image ...    */
 #define HSM_OPT_VALID_HI 4
 #define HSM_OPT_OUT_LO 5      /* ... and first/last local row this matcher owns (computes)           */
 #define HSM_OPT_OUT_HI 6
-#define HSM_OPT_FAST_DIV 7    /* 1 = shared-reciprocal correctly rounded division (default), 0 = div.rn.f32 */
+#define HSM_OPT_STAGES 7      /* shared-memory row stages of the TMA pipeline; 0 = as many (2..4) as fit      */
 
 typedef struct hsm_matcher hsm_matcher;
 
