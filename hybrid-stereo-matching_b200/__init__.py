@@ -6,6 +6,6 @@ The package directory is named after the project (``hybrid-stereo-matching_b200`
 ``importlib.import_module("hybrid-stereo-matching_b200")`` both give this package.
 """
 from ._capi import build_library, LIB_PATH      # noqa: F401
-from .mrf import StereoMRF                      # noqa: F401
+from .mrf import StereoMRF, pinned_empty        # noqa: F401
 
-__all__ = ["StereoMRF", "build_library", "LIB_PATH"]
+__all__ = ["StereoMRF", "pinned_empty", "build_library", "LIB_PATH"]

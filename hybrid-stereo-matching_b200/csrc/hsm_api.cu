@@ -68,33 +68,50 @@ struct LaneCfg {
     int lpp, vpl, nt;
 };
 
+// Table of lane configurations (index = HSM_OPT_LANE_CONFIG - 1).  Entries 0..5 are the
+// defaults per disparity range; 6..8 trade lanes per pixel for float4s per lane (fewer
+// shuffle steps and per-pixel operations per element, more registers per thread).
+const LaneCfg kLaneTable[] = {{4, 1, 256}, {8, 1, 256}, {16, 1, 512}, {32, 1, 512}, {32, 2, 512},
+                              {32, 4, 256}, {4, 2, 256}, {8, 2, 256}, {16, 2, 512}};
+constexpr int kLaneTableSize = 9;
+
+bool lane_cfg_fits(const LaneCfg &c, int D) { return D <= 4 * c.lpp * c.vpl; }
+
 bool lane_cfg(int D, LaneCfg *c)
 {
-    if (D <= 16) *c = {4, 1, 256};
-    else if (D <= 32) *c = {8, 1, 256};
-    else if (D <= 64) *c = {16, 1, 512};
-    else if (D <= 128) *c = {32, 1, 512};
-    else if (D <= 256) *c = {32, 2, 512};
-    else if (D <= 512) *c = {32, 4, 256};
+    int pick;
+    if (D <= 16) pick = 0;
+    else if (D <= 32) pick = 1;
+    else if (D <= 64) pick = 2;
+    else if (D <= 128) pick = 3;
+    else if (D <= 256) pick = 4;
+    else if (D <= 512) pick = 5;
     else return false;
+    *c = kLaneTable[pick];
     return true;
 }
 
 // Run `body` with LPP, VPL, NT as compile-time constants.
-#define HSM_DISPATCH(cfg, ...)                                                     \
-    do {                                                                           \
-        if ((cfg).lpp == 4) { constexpr int LPP = 4, VPL = 1, NT = 256; __VA_ARGS__ }          \
-        else if ((cfg).lpp == 8) { constexpr int LPP = 8, VPL = 1, NT = 256; __VA_ARGS__ }     \
-        else if ((cfg).lpp == 16) { constexpr int LPP = 16, VPL = 1, NT = 512; __VA_ARGS__ }   \
-        else if ((cfg).vpl == 1) { constexpr int LPP = 32, VPL = 1, NT = 512; __VA_ARGS__ }    \
-        else if ((cfg).vpl == 2) { constexpr int LPP = 32, VPL = 2, NT = 512; __VA_ARGS__ }    \
-        else { constexpr int LPP = 32, VPL = 4, NT = 256; __VA_ARGS__ }                        \
+#define HSM_DISPATCH_CASE(l, v, n, ...) \
+    if ((cfg__).lpp == l && (cfg__).vpl == v) { constexpr int LPP = l, VPL = v, NT = n; __VA_ARGS__ }
+#define HSM_DISPATCH(cfg, ...)                                  \
+    do {                                                        \
+        const LaneCfg cfg__ = (cfg);                            \
+        HSM_DISPATCH_CASE(4, 1, 256, __VA_ARGS__)               \
+        else HSM_DISPATCH_CASE(8, 1, 256, __VA_ARGS__)          \
+        else HSM_DISPATCH_CASE(16, 1, 512, __VA_ARGS__)         \
+        else HSM_DISPATCH_CASE(32, 1, 512, __VA_ARGS__)         \
+        else HSM_DISPATCH_CASE(32, 2, 512, __VA_ARGS__)         \
+        else HSM_DISPATCH_CASE(32, 4, 256, __VA_ARGS__)         \
+        else HSM_DISPATCH_CASE(4, 2, 256, __VA_ARGS__)          \
+        else HSM_DISPATCH_CASE(8, 2, 256, __VA_ARGS__)          \
+        else HSM_DISPATCH_CASE(16, 2, 512, __VA_ARGS__)         \
     } while (0)
 
 }  // namespace
 
 struct hsm_matcher {
-    int H = 0, W = 0, D = 0, Dp = 0, cap = 0, device = 0;
+    int H = 0, W = 0, Wp = 0, D = 0, Dp = 0, cap = 0, device = 0;
     LaneCfg cfg{};
     bool ready = false;
     cudaStream_t stream = nullptr;
@@ -112,9 +129,10 @@ struct hsm_matcher {
     bool have_fields = false, have_prior = false, dt_valid = false, s_valid = true;
     Blend blend{kPriorNone, 0.0f, 0.0};
     // options
-    int algorithm = 2, band_rows = 0, data_term = 1, stages = 0;
+    int algorithm = 2, band_rows = 0, data_term = 1, stages = 0, lane_config = 0;
     // TMA descriptors of the double-buffered planes (algorithm 2)
     CUtensorMap tmW[2], tmN[2], tmE[2], tmD;
+    ImageMaps tmI;
     bool maps_valid = false;
     int vlo = 0, vhi = 0, olo = 0, ohi = 0;
     // statistics
@@ -125,7 +143,7 @@ struct hsm_matcher {
 namespace {
 
 size_t plane_floats(const hsm_matcher *m) { return (size_t)m->cap * m->H * m->W * m->Dp; }
-size_t image_elems(const hsm_matcher *m) { return (size_t)m->cap * m->H * m->W; }
+size_t image_elems(const hsm_matcher *m) { return (size_t)m->cap * m->H * m->Wp; }
 
 size_t arena_layout(hsm_matcher *m, bool assign)
 {
@@ -174,10 +192,10 @@ int ensure_ready(hsm_matcher *m)
 Geo geometry(const hsm_matcher *m)
 {
     Geo g;
-    g.H = m->H; g.W = m->W; g.D = m->D; g.Dp = m->Dp;
+    g.H = m->H; g.W = m->W; g.Wp = m->Wp; g.D = m->D; g.Dp = m->Dp;
     g.vlo = m->vlo; g.vhi = m->vhi;
     g.plane_stride = (size_t)m->H * m->W * m->Dp;
-    g.image_stride = (size_t)m->H * m->W;
+    g.image_stride = (size_t)m->H * m->Wp;
     return g;
 }
 
@@ -239,14 +257,19 @@ int copy_in(hsm_matcher *m, void *dst, const void *src, size_t bytes, int on_dev
 
 int load_image(hsm_matcher *m, float *dst, const void *src, int dtype, int slot, size_t n, int on_device)
 {
-    if (dtype == HSM_F32) return copy_in(m, dst, src, n * 4, on_device);
+    if (dtype == HSM_F32) {
+        if (m->Wp == m->W) return copy_in(m, dst, src, n * 4, on_device);
+        CUDA_TRY(cudaMemcpy2DAsync(dst, (size_t)m->Wp * 4, src, (size_t)m->W * 4, (size_t)m->W * 4, n / m->W,
+                                   on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, m->stream));
+        return HSM_OK;
+    }
     const void *dev_src = src;
     if (!on_device) {
         HSM_TRY(copy_in(m, m->stage[slot], src, n * 8, 0));
         dev_src = m->stage[slot];
     }
     const int blocks = (int)std::min<size_t>((n + 255) / 256, (size_t)148 * 16);
-    k_to_f32<double><<<blocks, 256, 0, m->stream>>>((const double *)dev_src, dst, n);
+    k_to_f32<double><<<blocks, 256, 0, m->stream>>>((const double *)dev_src, dst, n, m->W, m->Wp);
     return check_launch(m, "k_to_f32");
 }
 
@@ -258,11 +281,12 @@ int load_prior(hsm_matcher *m, const void *src, int dtype, size_t n, int on_devi
         dev_src = m->stage[2];
     }
     const int blocks = (int)std::min<size_t>((n + 255) / 256, (size_t)148 * 16);
+    const int W = m->W, Wp = m->Wp;
     switch (dtype) {
-        case HSM_F32: k_prior_labels<float><<<blocks, 256, 0, m->stream>>>((const float *)dev_src, m->P, n, m->D); break;
-        case HSM_F64: k_prior_labels<double><<<blocks, 256, 0, m->stream>>>((const double *)dev_src, m->P, n, m->D); break;
-        case HSM_I32: k_prior_labels<int><<<blocks, 256, 0, m->stream>>>((const int *)dev_src, m->P, n, m->D); break;
-        case HSM_I64: k_prior_labels<long long><<<blocks, 256, 0, m->stream>>>((const long long *)dev_src, m->P, n, m->D); break;
+        case HSM_F32: k_prior_labels<float><<<blocks, 256, 0, m->stream>>>((const float *)dev_src, m->P, n, m->D, W, Wp); break;
+        case HSM_F64: k_prior_labels<double><<<blocks, 256, 0, m->stream>>>((const double *)dev_src, m->P, n, m->D, W, Wp); break;
+        case HSM_I32: k_prior_labels<int><<<blocks, 256, 0, m->stream>>>((const int *)dev_src, m->P, n, m->D, W, Wp); break;
+        case HSM_I64: k_prior_labels<long long><<<blocks, 256, 0, m->stream>>>((const long long *)dev_src, m->P, n, m->D, W, Wp); break;
         default: return fail(HSM_ERR_ARG, "unknown prior dtype %d", dtype);
     }
     return check_launch(m, "k_prior_labels");
@@ -298,15 +322,15 @@ int launch_fused(hsm_matcher *m, bool store_s)
     dim3 grid(strips, bands, m->frames);
     const bool dt_load = (m->data_term == 0);
     const bool full = (m->D == 4 * LPP * VPL);
-#define HSM_LAUNCH_FUSED(S, T, F) k_iter_fused<LPP, VPL, NT, S, T, F><<<grid, NT, 0, m->stream>>>(g, a)
+    a.store_s = store_s ? 1 : 0;
+    a.has_prior = m->have_prior ? 1 : 0;
     if (full) {
-        if (store_s) { if (dt_load) HSM_LAUNCH_FUSED(true, true, true); else HSM_LAUNCH_FUSED(true, false, true); }
-        else { if (dt_load) HSM_LAUNCH_FUSED(false, true, true); else HSM_LAUNCH_FUSED(false, false, true); }
+        if (dt_load) k_iter_fused<LPP, VPL, NT, true, true><<<grid, NT, 0, m->stream>>>(g, a);
+        else k_iter_fused<LPP, VPL, NT, false, true><<<grid, NT, 0, m->stream>>>(g, a);
     } else {
-        if (store_s) { if (dt_load) HSM_LAUNCH_FUSED(true, true, false); else HSM_LAUNCH_FUSED(true, false, false); }
-        else { if (dt_load) HSM_LAUNCH_FUSED(false, true, false); else HSM_LAUNCH_FUSED(false, false, false); }
+        if (dt_load) k_iter_fused<LPP, VPL, NT, true, false><<<grid, NT, 0, m->stream>>>(g, a);
+        else k_iter_fused<LPP, VPL, NT, false, false><<<grid, NT, 0, m->stream>>>(g, a);
     }
-#undef HSM_LAUNCH_FUSED
     HSM_TRY(check_launch(m, "k_iter_fused"));
     m->stats.iteration_launches++;
     m->cur ^= 1;
@@ -351,7 +375,24 @@ int make_plane_map(const hsm_matcher *m, CUtensorMap *map, float *plane, int px)
     return HSM_OK;
 }
 
-bool tma_supported(const hsm_matcher *m) { return m->Dp <= 256; }
+// 3-D map (cols, valid rows, frames) over a device image with row pitch Wp; box = `box` columns.
+int make_image_map(const hsm_matcher *m, CUtensorMap *map, void *image, bool is_int, int box)
+{
+    EncodeTiledFn encode;
+    HSM_TRY(encode_fn(&encode));
+    const cuuint64_t dims[3] = {(cuuint64_t)m->W, (cuuint64_t)(m->vhi - m->vlo + 1), (cuuint64_t)m->cap};
+    const cuuint64_t strides[2] = {(cuuint64_t)m->Wp * 4, (cuuint64_t)m->H * m->Wp * 4};
+    const cuuint32_t boxd[3] = {(cuuint32_t)box, 1, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    char *base = (char *)image + (size_t)m->vlo * m->Wp * 4;
+    CUresult rc = encode(map, is_int ? CU_TENSOR_MAP_DATA_TYPE_INT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims,
+                         strides, boxd, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS) return fail(HSM_ERR_CUDA, "cuTensorMapEncodeTiled (image) failed with code %d", (int)rc);
+    return HSM_OK;
+}
+
+bool tma_supported(const hsm_matcher *m) { return m->Dp <= 256 && m->cfg.lpp * m->cfg.vpl * 4 <= 256; }
 
 int ensure_maps(hsm_matcher *m)
 {
@@ -363,6 +404,12 @@ int ensure_maps(hsm_matcher *m)
         HSM_TRY(make_plane_map(m, &m->tmE[i], m->Em[i], px));
     }
     HSM_TRY(make_plane_map(m, &m->tmD, m->Dt, px));
+    // image segments: see StageLayout in iter_tma.cuh (LBOX, RSEG, RBOX)
+    const int dcov = 4 * m->cfg.lpp * m->cfg.vpl, rseg = px + dcov + 4;
+    const int rbox = rseg <= 256 ? rseg : ((rseg / 2 + 31) / 32 * 32);
+    HSM_TRY(make_image_map(m, &m->tmI.L, m->L, false, px + 4));
+    HSM_TRY(make_image_map(m, &m->tmI.R, m->R, false, rbox));
+    HSM_TRY(make_image_map(m, &m->tmI.P, m->P, true, px + 4));
     m->maps_valid = true;
     return HSM_OK;
 }
@@ -386,31 +433,29 @@ int launch_tma(hsm_matcher *m, bool store_s)
     dim3 grid(strips, bands, m->frames);
     const bool dt_load = (m->data_term == 0);
     const bool full = (m->D == 4 * LPP * VPL);
-    const size_t stage_bytes = (size_t)(dt_load ? 4 : 3) * PX * m->Dp * 4;
+    a.store_s = store_s ? 1 : 0;
+    a.has_prior = m->have_prior ? 1 : 0;
+    (void)PX;
+    const size_t stage_bytes = StageLayout<LPP, VPL, NT>::stage_bytes(m->Dp, dt_load);
     const size_t fixed_bytes = (size_t)2 * VPL * SLOTS * 16 + 64;
     int stages = m->stages;
-    if (stages <= 0) {      // as many stages (2..4) as fit the per-CTA share of shared memory
-        const int target_ctas = (NT == 256) ? 3 : (VPL == 1 ? 2 : 1);
+    if (stages <= 0) {      // as many stages (2..3) as fit the per-CTA share of shared memory
+        const int target_ctas = (NT == 256) ? (VPL == 1 ? 4 : 2) : (VPL == 1 ? 2 : 1);
         const size_t budget = (size_t)227 * 1024 / target_ctas - 1024;
-        stages = 4;
+        stages = 3;
         while (stages > 2 && fixed_bytes + stages * stage_bytes > budget) --stages;
     }
     const size_t smem = fixed_bytes + (size_t)stages * stage_bytes;
     if (smem > (size_t)227 * 1024) return fail(HSM_ERR_ARG, "fused TMA kernel needs %zu bytes of shared memory", smem);
     const CUtensorMap &tw = m->tmW[m->cur], &tn = m->tmN[m->cur], &te = m->tmE[m->cur], &td = m->tmD;
-#define HSM_LAUNCH_TMA(S, T, F)                                                                              \
+#define HSM_LAUNCH_TMA(T, F)                                                                                 \
     do {                                                                                                     \
-        auto kernel = k_iter_tma<LPP, VPL, NT, S, T, F>;                                                     \
+        auto kernel = k_iter_tma<LPP, VPL, NT, T, F>;                                                        \
         CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
-        kernel<<<grid, NT, smem, m->stream>>>(tw, tn, te, td, g, a, stages);                                 \
+        kernel<<<grid, NT, smem, m->stream>>>(tw, tn, te, td, m->tmI.L, m->tmI.R, m->tmI.P, g, a, stages);                         \
     } while (0)
-    if (full) {
-        if (store_s) { if (dt_load) HSM_LAUNCH_TMA(true, true, true); else HSM_LAUNCH_TMA(true, false, true); }
-        else { if (dt_load) HSM_LAUNCH_TMA(false, true, true); else HSM_LAUNCH_TMA(false, false, true); }
-    } else {
-        if (store_s) { if (dt_load) HSM_LAUNCH_TMA(true, true, false); else HSM_LAUNCH_TMA(true, false, false); }
-        else { if (dt_load) HSM_LAUNCH_TMA(false, true, false); else HSM_LAUNCH_TMA(false, false, false); }
-    }
+    if (full) { if (dt_load) HSM_LAUNCH_TMA(true, true); else HSM_LAUNCH_TMA(false, true); }
+    else { if (dt_load) HSM_LAUNCH_TMA(true, false); else HSM_LAUNCH_TMA(false, false); }
 #undef HSM_LAUNCH_TMA
     HSM_TRY(check_launch(m, "k_iter_tma"));
     m->stats.iteration_launches++;
@@ -486,7 +531,7 @@ int hsm_create(int rows, int cols, int n_levels, int capacity, int device, hsm_m
     if (!lane_cfg(n_levels, &cfg)) return fail(HSM_ERR_ARG, "n_levels %d > 512 is not supported", n_levels);
     if (capacity > 65535) return fail(HSM_ERR_ARG, "capacity %d > 65535", capacity);
     hsm_matcher *m = new hsm_matcher();
-    m->H = rows; m->W = cols; m->D = n_levels; m->Dp = (n_levels + 3) / 4 * 4;
+    m->H = rows; m->W = cols; m->Wp = (cols + 3) / 4 * 4; m->D = n_levels; m->Dp = (n_levels + 3) / 4 * 4;
     m->cap = capacity; m->device = device; m->cfg = cfg;
     m->vlo = 0; m->vhi = rows - 1; m->olo = 0; m->ohi = rows - 1;
     m->frames = 0;
@@ -547,6 +592,14 @@ int hsm_set_option(hsm_matcher *m, int key, int value)
             else if (key == HSM_OPT_OUT_LO) m->olo = value;
             else m->ohi = value;
             return HSM_OK;
+        case HSM_OPT_LANE_CONFIG: {
+            if (value < 0 || value > kLaneTableSize) return fail(HSM_ERR_ARG, "lane config %d out of range", value);
+            LaneCfg c;
+            if (value == 0) lane_cfg(m->D, &c); else c = kLaneTable[value - 1];
+            if (!lane_cfg_fits(c, m->D)) return fail(HSM_ERR_ARG, "lane config %d covers fewer than %d levels", value, m->D);
+            m->cfg = c; m->lane_config = value; m->maps_valid = false;
+            return HSM_OK;
+        }
         case HSM_OPT_STAGES:
             if (value < 0 || value > 8 || value == 1) return fail(HSM_ERR_ARG, "stages must be 0 (auto) or 2..8");
             m->stages = value; return HSM_OK;
@@ -566,6 +619,7 @@ int hsm_get_option(hsm_matcher *m, int key, int *value)
         case HSM_OPT_OUT_LO: *value = m->olo; return HSM_OK;
         case HSM_OPT_OUT_HI: *value = m->ohi; return HSM_OK;
         case HSM_OPT_STAGES: *value = m->stages; return HSM_OK;
+        case HSM_OPT_LANE_CONFIG: *value = m->lane_config; return HSM_OK;
         default: return fail(HSM_ERR_ARG, "unknown option %d", key);
     }
 }
@@ -574,7 +628,8 @@ int hsm_device_bytes(int rows, int cols, int n_levels, int capacity, size_t *byt
 {
     if (!bytes) return fail(HSM_ERR_ARG, "null bytes");
     hsm_matcher tmp;
-    tmp.H = rows; tmp.W = cols; tmp.D = n_levels; tmp.Dp = (n_levels + 3) / 4 * 4; tmp.cap = capacity;
+    tmp.H = rows; tmp.W = cols; tmp.Wp = (cols + 3) / 4 * 4; tmp.D = n_levels; tmp.Dp = (n_levels + 3) / 4 * 4;
+    tmp.cap = capacity;
     *bytes = arena_layout(&tmp, false);
     return HSM_OK;
 }

@@ -47,6 +47,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
             : "memory");
     } while (!done);
 }
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
 __device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2,
                                             int c3)
 {
@@ -60,12 +67,41 @@ __device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *map, u
 #define HSM_TMA_MIN_BLOCKS 3
 #endif
 
-template <int LPP, int VPL, int NT, bool STORE_S, bool DT_LOAD, bool FULL>
+// Byte size of one pipeline stage and where the image segments sit inside it (T24 only).
+template <int LPP, int VPL, int NT>
+struct StageLayout {
+    static constexpr int PX = NT / LPP;
+    static constexpr int DCOV = 4 * LPP * VPL;
+    // The innermost TMA coordinate must be 16-byte aligned, so image segments start at a column
+    // that is a multiple of 4 (up to 3 columns early) and are 4 columns longer than needed.
+    static constexpr int LBOX = PX + 4;                     // left image / prior: columns xs0 - 1 ..
+    static constexpr int RSEG = PX + DCOV + 4;              // right image: columns xs0 - DCOV .. xs0 + PX - 1
+    static constexpr int NRB = RSEG > 256 ? 2 : 1;          // TMA boxes are at most 256 elements wide
+    // two boxes: each a multiple of 32 floats so that the second one lands 128-byte aligned
+    static constexpr int RBOX = NRB == 1 ? RSEG : ((RSEG / 2 + 31) / 32 * 32);
+    static constexpr unsigned align128(unsigned v) { return (v + 127u) & ~127u; }
+    static constexpr unsigned L_BYTES = align128(LBOX * 4), R_BYTES = align128(NRB * RBOX * 4),
+                              P_BYTES = align128(LBOX * 4);
+    __host__ __device__ static unsigned planes_bytes(int Dp, bool dt_load) { return (dt_load ? 4u : 3u) * PX * Dp * 4u; }
+    __host__ __device__ static unsigned stage_bytes(int Dp, bool dt_load)
+    {
+        return planes_bytes(Dp, dt_load) + (dt_load ? 0u : (L_BYTES + R_BYTES + P_BYTES));
+    }
+};
+
+struct ImageMaps {
+    CUtensorMap L, R, P;
+};
+
+template <int LPP, int VPL, int NT, bool DT_LOAD, bool FULL>
 __global__ void __launch_bounds__(NT, (NT == 256 && VPL == 1) ? HSM_TMA_MIN_BLOCKS : 1)
     k_iter_tma(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmN,
-               const __grid_constant__ CUtensorMap tmE, const __grid_constant__ CUtensorMap tmD, Geo g, IterArgs a,
-               int stages)
+               const __grid_constant__ CUtensorMap tmE, const __grid_constant__ CUtensorMap tmD,
+               const __grid_constant__ CUtensorMap tmL, const __grid_constant__ CUtensorMap tmR,
+               const __grid_constant__ CUtensorMap tmP, Geo g, IterArgs a, int stages)
 {
+    using SL = StageLayout<LPP, VPL, NT>;
+    const bool STORE_S = a.store_s != 0;
     constexpr int PX = NT / LPP;
     constexpr int TX = PX - 2;
     constexpr int SLOTS = NT + 2 * LPP;
@@ -78,19 +114,20 @@ __global__ void __launch_bounds__(NT, (NT == 256 && VPL == 1) ? HSM_TMA_MIN_BLOC
     ln.init(tid % LPP, g.D, g.Dp);
 
     const unsigned row_floats = (unsigned)PX * (unsigned)g.Dp;          // one plane's row segment
-    float *stage_base = reinterpret_cast<float *>(smem_raw);
-    float4 *exch = reinterpret_cast<float4 *>(smem_raw + (size_t)stages * NPL * row_floats * 4);
+    const unsigned stage_bytes = SL::stage_bytes(g.Dp, DT_LOAD);
+    const unsigned planes_bytes = SL::planes_bytes(g.Dp, DT_LOAD);
+    float4 *exch = reinterpret_cast<float4 *>(smem_raw + (size_t)stages * stage_bytes);
     uint64_t *full = reinterpret_cast<uint64_t *>(exch + 2 * VPL * SLOTS);
     auto ex = [&](int par, int v, int slot) -> float4 & { return exch[(par * VPL + v) * SLOTS + slot]; };
 
     const int xs0 = (int)blockIdx.x * TX;
+    const int shift_l = (xs0 - 1) & 3, shift_r = (xs0 - SL::DCOV) & 3;    // see StageLayout
     const int x = xs0 - 1 + px;
     const bool in_x = (x >= 0 && x < g.W);
     const int yb0 = a.olo + (int)blockIdx.y * a.band_rows;
     const int yb1 = min(yb0 + a.band_rows - 1, a.ohi);
     const int frame = (int)blockIdx.z;
     const size_t fplane = (size_t)frame * g.plane_stride;
-    const size_t fimage = (size_t)frame * g.image_stride;
     const unsigned row_stride = (unsigned)g.W * (unsigned)g.Dp;
     const int n_rows = yb1 - yb0 + 3;                                    // rows yb0-1 .. yb1+1
 
@@ -112,12 +149,25 @@ __global__ void __launch_bounds__(NT, (NT == 256 && VPL == 1) ? HSM_TMA_MIN_BLOC
     // producer side (thread 0): one bulk tensor copy per plane into stage s for row index r
     auto issue = [&](int r, int s) {
         const int yy = yb0 - 1 + r - g.vlo;            // row coordinate inside the valid-row tensor
-        float *dst = stage_base + (size_t)s * NPL * row_floats;
-        mbar_expect_tx(&full[s], NPL * row_floats * 4u);
+        unsigned char *stage_ptr = smem_raw + (size_t)s * stage_bytes;
+        float *dst = reinterpret_cast<float *>(stage_ptr);
+        unsigned tx = NPL * row_floats * 4u;
+        if (!DT_LOAD) tx += SL::LBOX * 4u + SL::NRB * SL::RBOX * 4u + (a.has_prior ? SL::LBOX * 4u : 0u);
+        mbar_expect_tx(&full[s], tx);
         tma_load_4d(dst, &tmW, &full[s], 0, xs0 - 1, yy, frame);
         tma_load_4d(dst + row_floats, &tmN, &full[s], 0, xs0 - 1, yy, frame);
         tma_load_4d(dst + 2 * row_floats, &tmE, &full[s], 0, xs0 - 1, yy, frame);
-        if (DT_LOAD) tma_load_4d(dst + 3 * row_floats, &tmD, &full[s], 0, xs0 - 1, yy, frame);
+        if (DT_LOAD) {
+            tma_load_4d(dst + 3 * row_floats, &tmD, &full[s], 0, xs0 - 1, yy, frame);
+        } else {
+            unsigned char *img = stage_ptr + planes_bytes;
+            tma_load_3d(img, &tmL, &full[s], xs0 - 1 - shift_l, yy, frame);
+#pragma unroll
+            for (int b = 0; b < SL::NRB; ++b)
+                tma_load_3d(img + SL::L_BYTES + b * SL::RBOX * 4, &tmR, &full[s],
+                            xs0 - SL::DCOV - shift_r + b * SL::RBOX, yy, frame);
+            if (a.has_prior) tma_load_3d(img + SL::L_BYTES + SL::R_BYTES, &tmP, &full[s], xs0 - 1 - shift_l, yy, frame);
+        }
     };
     if (tid == 0) {
         const int first = n_rows < stages ? n_rows : stages;
@@ -125,7 +175,7 @@ __global__ void __launch_bounds__(NT, (NT == 256 && VPL == 1) ? HSM_TMA_MIN_BLOC
     }
 
     float *Wout = a.Wout + fplane, *Nout = a.Nout + fplane, *Eout = a.Eout + fplane;
-    float *Sout = STORE_S ? a.Sout + fplane : nullptr;
+    float *Sout = a.Sout + fplane;
 
     RowRegs<VPL> cur;
     Vec<VPL> Scur, Xprev, Dprev;
@@ -138,7 +188,8 @@ __global__ void __launch_bounds__(NT, (NT == 256 && VPL == 1) ? HSM_TMA_MIN_BLOC
     // consumer side: wait for row index r, copy this lane's chunks of the stage to registers
     auto fetch = [&](int y) {
         mbar_wait(&full[stage], phase);
-        const float4 *sp = reinterpret_cast<const float4 *>(stage_base + (size_t)stage * NPL * row_floats) + lane_f4;
+        const unsigned char *stage_ptr = smem_raw + (size_t)stage * stage_bytes;
+        const float4 *sp = reinterpret_cast<const float4 *>(stage_ptr) + lane_f4;
         const unsigned plane_f4 = row_floats / 4;
 #pragma unroll
         for (int v = 0; v < VPL; ++v) {
@@ -153,8 +204,11 @@ __global__ void __launch_bounds__(NT, (NT == 256 && VPL == 1) ? HSM_TMA_MIN_BLOC
             }
         }
         if (!DT_LOAD) {
-            const bool valid = in_x && y >= g.vlo && y <= g.vhi;
-            data_vec<LPP, VPL>(cur.d, ln, a.L, a.R, a.P, fimage + (size_t)(valid ? y : 0) * g.W, x, g.D, a.blend, valid);
+            const unsigned char *img = stage_ptr + planes_bytes;
+            data_vec_smem<LPP, VPL, FULL>(cur.d, ln, reinterpret_cast<const float *>(img) + shift_l,
+                                          reinterpret_cast<const float *>(img + SL::L_BYTES) + shift_r,
+                                          reinterpret_cast<const int *>(img + SL::L_BYTES + SL::R_BYTES) + shift_l, px,
+                                          x, in_x, g.D, a.blend, a.has_prior != 0);
         }
     };
     // after the row's barrier: the stage is free, refill it with row index r + stages

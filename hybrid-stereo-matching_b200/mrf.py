@@ -13,6 +13,7 @@ Differences that are deliberate and invisible to the reference's callers:
   * extra, optional surface: ``capacity`` (frames per launch) and ``lbp_batch``.
 """
 import ctypes
+import weakref
 
 import numpy as np
 
@@ -39,6 +40,35 @@ def _as_prior(array):
         array = array.astype(np.float64 if array.dtype.kind == "f" else np.int64)
     array = np.ascontiguousarray(array)
     return array, _PRIOR_CODES[array.dtype]
+
+
+def pinned_empty(shape, dtype):
+    """numpy array backed by page-locked host memory (cudaHostAlloc through the C ABI), for
+    asynchronous transfers in ``lbp_batch``.  Freed when the array is garbage collected."""
+    dtype = np.dtype(dtype)
+    count = int(np.prod(shape))
+    pointer = ctypes.c_void_p()
+    nbytes = max(count * dtype.itemsize, 1)
+    _capi.check(_capi.lib().hsm_host_alloc(nbytes, ctypes.byref(pointer)))
+    address = pointer.value
+    buffer = (ctypes.c_char * nbytes).from_address(address)
+    # every numpy view keeps `buffer` alive; release the pinned block when the last one goes
+    weakref.finalize(buffer, lambda: _capi.lib().hsm_host_free(ctypes.c_void_p(address)))
+    return np.frombuffer(buffer, dtype=dtype, count=count).reshape(shape)
+
+
+_CAI_CODES = {"<f4": _capi.F32, "<f8": _capi.F64, "<i4": _capi.I32, "<i8": _capi.I64}
+
+
+def _device_array(obj, what):
+    """(pointer, dtype code, shape) of a CUDA array (anything with __cuda_array_interface__,
+    e.g. a torch tensor -- used as a container only)."""
+    cai = obj.__cuda_array_interface__
+    if cai.get("strides") is not None:
+        raise ValueError("%s must be C-contiguous" % what)
+    if cai["typestr"] not in _CAI_CODES:
+        raise ValueError("%s has unsupported dtype %s" % (what, cai["typestr"]))
+    return cai["data"][0], _CAI_CODES[cai["typestr"]], tuple(cai["shape"])
 
 
 def _blend(prior, prior_trust_factor, prior_influence_mode):
@@ -178,25 +208,82 @@ class StereoMRF(object):
         return self.get_map_belief()
 
     # ----------------------------------------------------------------- extensions
+    def _lanes(self, count):
+        """This matcher plus helper matchers of the same geometry (own stream, own device
+        buffers), so that one lane's host<->device copies overlap another lane's kernels."""
+        lanes = getattr(self, "_helper_lanes", None)
+        if lanes is None:
+            lanes = self._helper_lanes = []
+        while len(lanes) < count - 1:
+            helper = StereoMRF((self._rows, self._cols), self.n_levels, self.capacity, self.device)
+            for key in (_capi.OPT_LANE_CONFIG, _capi.OPT_ALGORITHM, _capi.OPT_BAND_ROWS, _capi.OPT_DATA_TERM,
+                        _capi.OPT_STAGES):
+                helper.set_option(key, self.get_option(key))
+            lanes.append(helper)
+        return [self] + lanes[:count - 1]
+
     def lbp_batch(self, images_left, images_right, priors=None, prior_trust_factor=0.5,
-                  prior_influence_mode="const", n_iter=10):
+                  prior_influence_mode="const", n_iter=10, out=None, lanes=2):
         """``lbp`` over a stack of independent frame pairs ``(N, H, W)`` -> ``(N, H, W)`` int64.
 
-        Frames are processed ``capacity`` at a time; each frame's result equals
-        what ``lbp`` returns for it alone (every call re-initialises, mrf.py:165).
+        Frames are processed ``capacity`` at a time, alternating between ``lanes`` matchers
+        so that transfers overlap compute (fully so when the arrays are page-locked, see
+        ``pinned_empty``).  Each frame's result equals what ``lbp`` returns for it alone
+        (every call re-initialises the messages, mrf.py:165).
         """
         images_left, images_right = np.asarray(images_left), np.asarray(images_right)
         priors = None if priors is None else np.asarray(priors)
         assert images_left.ndim == 3 and images_left.shape == images_right.shape
         n_total = images_left.shape[0]
-        out = np.empty((n_total, self._rows, self._cols), dtype=np.int64)
-        for start in range(0, n_total, self.capacity):
-            stop = min(start + self.capacity, n_total)
-            self._init_fields(images_left[start:stop], images_right[start:stop],
+        if out is None:
+            out = np.empty((n_total, self._rows, self._cols), dtype=np.int64)
+        assert out.shape == (n_total, self._rows, self._cols) and out.dtype == np.int64 \
+            and out.flags["C_CONTIGUOUS"]
+        chunks = [(start, min(start + self.capacity, n_total)) for start in range(0, n_total, self.capacity)]
+        workers = self._lanes(max(1, min(int(lanes), len(chunks))))
+        for index, (start, stop) in enumerate(chunks):
+            lane = workers[index % len(workers)]
+            lane.synchronize()
+            lane._init_fields(images_left[start:stop], images_right[start:stop],
                               None if priors is None else priors[start:stop],
                               prior_trust_factor, prior_influence_mode, True, _batched=True)
-            _capi.check(_capi.lib().hsm_iterate(self._handle, int(n_iter), 1))
-            out[start:stop] = self._readout()
+            _capi.check(_capi.lib().hsm_iterate(lane._handle, int(n_iter), 1))
+            target = out[start:stop]
+            _capi.check(_capi.lib().hsm_readout(lane._handle, target.ctypes.data_as(ctypes.c_void_p), 0, 1))
+        for lane in workers:
+            lane.synchronize()
+        self._belief_field_cache = out[chunks[-1][0]:chunks[-1][1]] if chunks else out
+        return out
+
+    def lbp_batch_device(self, images_left, images_right, priors, out, prior_trust_factor=0.5,
+                         prior_influence_mode="const", n_iter=10, synchronize=True):
+        """``lbp`` for ``N <= capacity`` frame pairs that already live on this GPU.
+
+        The arguments are CUDA arrays (``__cuda_array_interface__``: torch tensors, cupy
+        arrays) used purely as containers: images float32/float64 ``(N, H, W)``, priors
+        None or float/int ``(N, H, W)``, ``out`` int64 ``(N, H, W)``.  Work is queued on the
+        matcher's stream (see ``set_stream``).
+        """
+        left_ptr, code, shape = _device_array(images_left, "images_left")
+        right_ptr, code_r, shape_r = _device_array(images_right, "images_right")
+        assert shape == shape_r and len(shape) == 3
+        if shape[1:] != (self._rows, self._cols):
+            raise ValueError("could not broadcast input array from shape %r into shape %r"
+                             % (shape[1:], (self._rows, self._cols)))
+        if code != code_r or code not in (_capi.F32, _capi.F64):
+            raise ValueError("device images must both be float32 or both be float64")
+        out_ptr, out_code, out_shape = _device_array(out, "out")
+        assert out_code == _capi.I64 and out_shape == shape
+        mode, keep32, keep64 = _blend(priors, prior_trust_factor, prior_influence_mode)
+        prior_ptr, prior_code = None, _capi.F32
+        if priors is not None:
+            prior_ptr, prior_code, prior_shape = _device_array(priors, "priors")
+            assert prior_shape == shape
+        _capi.check(_capi.lib().hsm_lbp(
+            self._handle, shape[0], ctypes.c_void_p(left_ptr), ctypes.c_void_p(right_ptr), code,
+            ctypes.c_void_p(prior_ptr) if prior_ptr else None, prior_code, mode, keep32, keep64,
+            int(n_iter), ctypes.c_void_p(out_ptr), 1, 0 if synchronize else 1))
+        self._frames, self._batched = shape[0], True
         return out
 
     # ------------------------------------------------------- read-back accessors

@@ -61,7 +61,8 @@ extern "C" {
 #define HSM_OPT_VALID_HI 4
 #define HSM_OPT_OUT_LO 5      /* ... and first/last local row this matcher owns (computes)           */
 #define HSM_OPT_OUT_HI 6
-#define HSM_OPT_STAGES 7      /* shared-memory row stages of the TMA pipeline; 0 = as many (2..4) as fit      */
+#define HSM_OPT_STAGES 7      /* shared-memory row stages of the TMA pipeline; 0 = automatic (2..3)          */
+#define HSM_OPT_LANE_CONFIG 8 /* tuning: 0 = default lanes-per-pixel layout for n_levels, 1..9 = table entry  */
 
 typedef struct hsm_matcher hsm_matcher;
 
@@ -86,7 +87,9 @@ int hsm_device_count(int *count);
 int hsm_create(int rows, int cols, int n_levels, int capacity, int device, hsm_matcher **out);
 int hsm_destroy(hsm_matcher *m);
 
-/* Use the caller's CUDA stream (a cudaStream_t passed as void*) instead of the matcher's own. */
+/* Use the caller's CUDA stream (a cudaStream_t passed as void*) instead of the matcher's own
+ * non-blocking stream; NULL goes back to the matcher's own stream.  (To run on the legacy
+ * default stream pass cudaStreamLegacy, not NULL.) */
 int hsm_set_stream(hsm_matcher *m, void *cuda_stream);
 int hsm_set_option(hsm_matcher *m, int key, int value);
 int hsm_get_option(hsm_matcher *m, int key, int *value);
