@@ -177,7 +177,7 @@ def main():
     parser.add_argument("--warmup", type=int, default=3)
     parser.add_argument("--impl", default="b200", choices=["b200", "reference"])
     parser.add_argument("--frames-per-step", type=int, default=256, help="frame pairs per GPU per step")
-    parser.add_argument("--capacity", type=int, default=64, help="frame pairs per launch (device batch)")
+    parser.add_argument("--capacity", type=int, default=128, help="frame pairs per launch (device batch)")
     parser.add_argument("--cpu-frames", type=int, default=10, help="frames of the CPU baseline sample (0 = skip)")
     args = parser.parse_args()
     args.warmup = max(args.warmup, 0)

@@ -1,0 +1,161 @@
+"""Row-band partitioning of ONE large frame across GPUs (BASELINE.json configs[4]).
+
+The reference has no multi-device path; this is the spatial analogue the north star asks
+for.  Rank ``r`` of ``G`` owns a contiguous band of image rows and
+keeps one ghost row above and below it.  Because a fused iteration needs only the OLD
+west / north / east mailboxes of the 3x3 neighbourhood, one exchange
+per iteration is enough: after iteration ``k`` every rank sends its first and last owned
+rows of the three planes to its vertical neighbours, which store them in their ghost rows
+before iteration ``k + 1``.  The result is bit-identical to the single-GPU run.
+
+The protocol (who owns which rows, what is exchanged when) is independent of the engine
+that does the arithmetic, so the CPU test-suite drives it with a numpy engine over gloo and
+the GPU path drives the CUDA matcher over NCCL (``torch.distributed`` point-to-point; the
+halo is 3 x W x Dp floats each way, e.g. 5.9 MB at 1920 x D256 -- latency-, not
+bandwidth-bound on NVLink).
+"""
+import ctypes
+
+import numpy as np
+
+from . import _capi
+
+
+def band_bounds(n_rows, world, rank):
+    """First and last image row (inclusive) owned by ``rank``: contiguous, sizes differ by <= 1."""
+    base, extra = divmod(int(n_rows), int(world))
+    if base == 0:
+        raise ValueError("more ranks (%d) than image rows (%d)" % (world, n_rows))
+    first = rank * base + min(rank, extra)
+    last = first + base - 1 + (1 if rank < extra else 0)
+    return first, last
+
+
+def frames_for_rank(n_frames, world, rank):
+    """Indices of the frames of a sequence processed by ``rank`` (frame sharding, no collective)."""
+    return list(range(int(rank), int(n_frames), int(world)))
+
+
+class CudaBandEngine(object):
+    """The CUDA matcher as a band engine: local rows = [ghost above] + owned + [ghost below]."""
+
+    def __init__(self, n_rows, n_cols, n_levels, first, last, device=0):
+        import torch                                  # container for the halo buffers only
+        from .mrf import StereoMRF
+        self.torch = torch
+        self.first, self.last, self.n_rows = first, last, n_rows
+        self.own = last - first + 1
+        self.local_rows = self.own + 2
+        self.matcher = StereoMRF((self.local_rows, n_cols), n_levels, capacity=1, device=device)
+        self.matcher.set_option(_capi.OPT_OUT_LO, 1)
+        self.matcher.set_option(_capi.OPT_OUT_HI, self.own)
+        self.matcher.set_option(_capi.OPT_VALID_LO, 0 if first > 0 else 1)
+        self.matcher.set_option(_capi.OPT_VALID_HI, self.own + 1 if last < n_rows - 1 else self.own)
+        # kernels, halo copies and the NCCL point-to-point ops are all ordered on this stream
+        self.stream = torch.cuda.Stream(device=device)
+        self.matcher.set_stream(self.stream.cuda_stream)
+        count = ctypes.c_size_t()
+        _capi.check(_capi.lib().hsm_halo_floats(self.matcher._handle, ctypes.byref(count)))
+        self.halo_floats = count.value
+        self.device = torch.device("cuda", device)
+
+    def stream_context(self):
+        return self.torch.cuda.stream(self.stream)
+
+    def _local(self, image):
+        """Rows first-1 .. last+1 of a full image, zero rows where that is outside the image."""
+        image = np.asarray(image)
+        out = np.zeros((self.local_rows,) + image.shape[1:], dtype=image.dtype)
+        lo, hi = max(self.first - 1, 0), min(self.last + 1, self.n_rows - 1)
+        out[lo - (self.first - 1):hi - (self.first - 1) + 1] = image[lo:hi + 1]
+        return out
+
+    def init_fields(self, image_left, image_right, prior, prior_trust_factor, prior_influence_mode):
+        local_prior = None
+        if prior is not None:
+            local_prior = self._local(prior)
+            if self.first == 0:
+                local_prior[0] = -1
+            if self.last == self.n_rows - 1:
+                local_prior[-1] = -1
+        self.matcher._init_fields(self._local(image_left), self._local(image_right), local_prior,
+                                  prior_trust_factor, prior_influence_mode, True)
+
+    def iterate(self, finalize):
+        _capi.check(_capi.lib().hsm_iterate(self.matcher._handle, 1, 1 if finalize else 0))
+
+    def new_halo(self):
+        return self.torch.empty(self.halo_floats, dtype=self.torch.float32, device=self.device)
+
+    def pack(self, top, bottom):
+        _capi.check(_capi.lib().hsm_halo_pack(self.matcher._handle,
+                                              ctypes.c_void_p(top.data_ptr()) if top is not None else None,
+                                              ctypes.c_void_p(bottom.data_ptr()) if bottom is not None else None))
+
+    def unpack(self, from_above, from_below):
+        _capi.check(_capi.lib().hsm_halo_unpack(
+            self.matcher._handle,
+            ctypes.c_void_p(from_above.data_ptr()) if from_above is not None else None,
+            ctypes.c_void_p(from_below.data_ptr()) if from_below is not None else None))
+
+    def labels(self):
+        return self.matcher.get_map_belief()[1:self.own + 1]
+
+    def planes(self):
+        """Owned rows of the five planes, reference layout (D, own rows, W)."""
+        return {name: plane[:, 1:self.own + 1, :] for name, plane in self.matcher._message_field.items()}
+
+
+class RowBandMatcher(object):
+    """``lbp`` of one frame split into row bands over the ranks of a process group.
+
+    ``engine`` does the arithmetic on this rank's band (``CudaBandEngine`` in production).
+    Every rank passes the full images; ``lbp`` returns this rank's rows of the disparity map
+    and ``gather`` assembles the full map on every rank.
+    """
+
+    def __init__(self, engine, rank, world, group=None):
+        self.engine, self.rank, self.world, self.group = engine, int(rank), int(world), group
+        self._send_up = self._send_down = self._recv_up = self._recv_down = None
+
+    def _exchange(self):
+        import torch.distributed as dist
+        eng = self.engine
+        up, down = self.rank - 1, self.rank + 1
+        has_up, has_down = up >= 0, down < self.world
+        if self._send_up is None:
+            self._send_up, self._send_down = eng.new_halo(), eng.new_halo()
+            self._recv_up, self._recv_down = eng.new_halo(), eng.new_halo()
+        eng.pack(self._send_up if has_up else None, self._send_down if has_down else None)
+        ops = []
+        if has_up:
+            ops.append(dist.P2POp(dist.isend, self._send_up, up, self.group))
+            ops.append(dist.P2POp(dist.irecv, self._recv_up, up, self.group))
+        if has_down:
+            ops.append(dist.P2POp(dist.isend, self._send_down, down, self.group))
+            ops.append(dist.P2POp(dist.irecv, self._recv_down, down, self.group))
+        if ops:
+            for request in dist.batch_isend_irecv(ops):
+                request.wait()
+        eng.unpack(self._recv_up if has_up else None, self._recv_down if has_down else None)
+
+    def lbp(self, image_left, image_right, prior=None, prior_trust_factor=0.5,
+            prior_influence_mode="const", n_iter=10):
+        with self.engine.stream_context():
+            self.engine.init_fields(image_left, image_right, prior, prior_trust_factor, prior_influence_mode)
+            for iteration in range(int(n_iter)):
+                last = iteration == int(n_iter) - 1
+                self.engine.iterate(finalize=last)
+                if not last and self.world > 1:
+                    self._exchange()
+            return self.engine.labels()
+
+    def gather(self, local_labels):
+        """Full (H, W) int64 disparity map on every rank."""
+        import torch
+        import torch.distributed as dist
+        if self.world == 1:
+            return np.asarray(local_labels)
+        pieces = [None] * self.world
+        dist.all_gather_object(pieces, np.asarray(local_labels), group=self.group)
+        return np.concatenate(pieces, axis=0)

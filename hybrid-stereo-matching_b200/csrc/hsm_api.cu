@@ -82,7 +82,7 @@ bool lane_cfg(int D, LaneCfg *c)
     int pick;
     if (D <= 16) pick = 0;
     else if (D <= 32) pick = 1;
-    else if (D <= 64) pick = 2;
+    else if (D <= 64) pick = 7;        // 8 lanes x 2 float4: measured faster than 16 x 1 at 640x480xD64
     else if (D <= 128) pick = 3;
     else if (D <= 256) pick = 4;
     else if (D <= 512) pick = 5;
@@ -296,8 +296,9 @@ int choose_band_rows(const hsm_matcher *m, int strips)
 {
     const int rows = m->ohi - m->olo + 1;
     if (m->band_rows > 0) return std::min(m->band_rows, rows);
-    // aim for ~8 CTAs per SM over the whole launch, bands of at least 12 rows (2 halo rows per band)
-    const long target = 148L * 8;
+    // aim for ~16 CTAs per SM over the whole launch (several waves, short tail), bands of at
+    // least 12 rows (each band re-reads 2 halo rows)
+    const long target = 148L * 16;
     const long per_band = (long)strips * m->frames;
     long bands = (target + per_band - 1) / per_band;
     bands = std::max(1L, std::min<long>(bands, std::max(1, rows / 12)));
@@ -437,7 +438,7 @@ int launch_tma(hsm_matcher *m, bool store_s)
     a.has_prior = m->have_prior ? 1 : 0;
     (void)PX;
     const size_t stage_bytes = StageLayout<LPP, VPL, NT>::stage_bytes(m->Dp, dt_load);
-    const size_t fixed_bytes = (size_t)2 * VPL * SLOTS * 16 + 64;
+    const size_t fixed_bytes = (size_t)2 * VPL * SLOTS * 16 + 128;   // exchange slots + mbarriers
     int stages = m->stages;
     if (stages <= 0) {      // as many stages (2..3) as fit the per-CTA share of shared memory
         const int target_ctas = (NT == 256) ? (VPL == 1 ? 4 : 2) : (VPL == 1 ? 2 : 1);

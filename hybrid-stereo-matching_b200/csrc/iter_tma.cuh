@@ -34,6 +34,10 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 {
     uint32_t done;
@@ -118,6 +122,7 @@ __global__ void __launch_bounds__(NT, (NT == 256 && VPL == 1) ? HSM_TMA_MIN_BLOC
     const unsigned planes_bytes = SL::planes_bytes(g.Dp, DT_LOAD);
     float4 *exch = reinterpret_cast<float4 *>(smem_raw + (size_t)stages * stage_bytes);
     uint64_t *full = reinterpret_cast<uint64_t *>(exch + 2 * VPL * SLOTS);
+    uint64_t *xbar = full + stages;                                      // W' exchange barrier (all NT threads)
     auto ex = [&](int par, int v, int slot) -> float4 & { return exch[(par * VPL + v) * SLOTS + slot]; };
 
     const int xs0 = (int)blockIdx.x * TX;
@@ -138,6 +143,7 @@ __global__ void __launch_bounds__(NT, (NT == 256 && VPL == 1) ? HSM_TMA_MIN_BLOC
 
     if (tid == 0) {
         for (int s = 0; s < stages; ++s) mbar_init(&full[s], 1);
+        mbar_init(xbar, NT);
         mbar_fence_init();
     }
     if (tid < 2 * LPP) {
@@ -177,103 +183,123 @@ __global__ void __launch_bounds__(NT, (NT == 256 && VPL == 1) ? HSM_TMA_MIN_BLOC
     float *Wout = a.Wout + fplane, *Nout = a.Nout + fplane, *Eout = a.Eout + fplane;
     float *Sout = a.Sout + fplane;
 
-    RowRegs<VPL> cur;
-    Vec<VPL> Scur, Xprev, Dprev;
+    // ---- consumer side ------------------------------------------------------------------------
+    // Carried between rows (two copies each, alternating per row so that no register moves are
+    // needed): S'(y, x), X(y-1, x) = S'(y-1, x) + W'(y-1, x), data term of row y-1.
+    Vec<VPL> S0, S1, X0, X1, D0, D1;
 #pragma unroll
-    for (int v = 0; v < VPL; ++v) Scur.q[v] = Xprev.q[v] = Dprev.q[v] = cur.d.q[v] = zero4();
+    for (int v = 0; v < VPL; ++v) S0.q[v] = S1.q[v] = X0.q[v] = X1.q[v] = D0.q[v] = D1.q[v] = zero4();
 
     const unsigned lane_f4 = (unsigned)px * (unsigned)(g.Dp / 4) + (unsigned)ln.c;   // float4 index in a row segment
+    const unsigned plane_f4 = row_floats / 4;
+    const float4 *lane_base = reinterpret_cast<const float4 *>(smem_raw) + lane_f4;
+    const unsigned char *img_base = smem_raw + planes_bytes;
     int stage = 0;
-    uint32_t phase = 0;
-    // consumer side: wait for row index r, copy this lane's chunks of the stage to registers
-    auto fetch = [&](int y) {
+    uint32_t phase = 0, xphase = 0;
+    // element offset of (row y, this lane's pixel and chunk) inside the frame; advanced by one row per step
+    // (x may be -1 or W for halo lanes: the wrap-around cancels when the neighbour offset is added)
+    unsigned row_off = (unsigned)yb0 * row_stride + (unsigned)x * (unsigned)g.Dp + 4u * (unsigned)ln.c;
+
+    // wait for the stage holding row y, copy this lane's chunks to registers, build the data term
+    auto fetch = [&](Vec<VPL> &w, Vec<VPL> &n, Vec<VPL> &e, Vec<VPL> &d) {
         mbar_wait(&full[stage], phase);
-        const unsigned char *stage_ptr = smem_raw + (size_t)stage * stage_bytes;
-        const float4 *sp = reinterpret_cast<const float4 *>(stage_ptr) + lane_f4;
-        const unsigned plane_f4 = row_floats / 4;
+        const unsigned stage_off = (unsigned)stage * stage_bytes;
+        const float4 *sp = reinterpret_cast<const float4 *>(reinterpret_cast<const unsigned char *>(lane_base) + stage_off);
 #pragma unroll
         for (int v = 0; v < VPL; ++v) {
             if (FULL || ln.active[v]) {
-                cur.w.q[v] = sp[v * LPP];
-                cur.n.q[v] = sp[plane_f4 + v * LPP];
-                cur.e.q[v] = sp[2 * plane_f4 + v * LPP];
-                if (DT_LOAD) cur.d.q[v] = sp[3 * plane_f4 + v * LPP];
+                w.q[v] = sp[v * LPP];
+                n.q[v] = sp[plane_f4 + v * LPP];
+                e.q[v] = sp[2 * plane_f4 + v * LPP];
+                if (DT_LOAD) d.q[v] = sp[3 * plane_f4 + v * LPP];
             } else {
-                cur.w.q[v] = cur.n.q[v] = cur.e.q[v] = zero4();
-                if (DT_LOAD) cur.d.q[v] = zero4();
+                w.q[v] = n.q[v] = e.q[v] = zero4();
+                if (DT_LOAD) d.q[v] = zero4();
             }
         }
         if (!DT_LOAD) {
-            const unsigned char *img = stage_ptr + planes_bytes;
-            data_vec_smem<LPP, VPL, FULL>(cur.d, ln, reinterpret_cast<const float *>(img) + shift_l,
+            const unsigned char *img = img_base + stage_off;
+            data_vec_smem<LPP, VPL, FULL>(d, ln, reinterpret_cast<const float *>(img) + shift_l,
                                           reinterpret_cast<const float *>(img + SL::L_BYTES) + shift_r,
                                           reinterpret_cast<const int *>(img + SL::L_BYTES + SL::R_BYTES) + shift_l, px,
                                           x, in_x, g.D, a.blend, a.has_prior != 0);
         }
     };
-    // after the row's barrier: the stage is free, refill it with row index r + stages
+    // every thread has copied the current stage: refill it with row index r + stages
     auto refill = [&](int r) {
         if (tid == 0 && r + stages < n_rows) issue(r + stages, stage);
         if (++stage == stages) { stage = 0; phase ^= 1u; }
     };
-    auto store_vec = [&](float *plane, int y, int xx, const Vec<VPL> &val) {
-        const unsigned off = (unsigned)y * row_stride + (unsigned)xx * (unsigned)g.Dp + 4u * (unsigned)ln.c;
+    auto store_at = [&](float *plane, unsigned off, const Vec<VPL> &val) {
 #pragma unroll
         for (int v = 0; v < VPL; ++v)
             if (FULL || ln.active[v]) st_plain(plane + off + 4 * LPP * v, val.q[v]);
     };
 
     // row yb0-1 only contributes S'(yb0)
-    fetch(yb0 - 1);
+    {
+        Vec<VPL> w, n, e, d;
 #pragma unroll
-    for (int v = 0; v < VPL; ++v) Scur.q[v] = sum4(cur.w.q[v], cur.n.q[v], cur.e.q[v], cur.d.q[v]);
-    normalise<LPP, VPL, FULL>(Scur, ln);
-    if (STORE_S && st_n) store_vec(Sout, yb0, x, Scur);
-    __syncthreads();
-    refill(0);
+        for (int v = 0; v < VPL; ++v) d.q[v] = zero4();
+        fetch(w, n, e, d);
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) S0.q[v] = sum4(w.q[v], n.q[v], e.q[v], d.q[v]);
+        normalise<LPP, VPL, FULL>(S0, ln);
+        if (STORE_S && st_n) store_at(Sout, row_off, S0);
+        __syncthreads();
+        refill(0);
+    }
 
-    int par = 0;
-    for (int y = yb0; y <= yb1 + 1; ++y) {
-        fetch(y);
-        if (y > g.vhi) {
+    // One row: Sin = S'(y, x); Xin, Din belong to row y-1; Sout_/Xout/Dout are produced for the next row.
+    // The exchange of W' uses a split barrier: arrive after publishing W'(y, x-1), compute S'(y+1)
+    // (which does not depend on the neighbour), then wait and pick up W'(y, x).
+    auto step = [&](int y, const int par, Vec<VPL> &Sin, Vec<VPL> &Snext, const Vec<VPL> &Xin, Vec<VPL> &Xout,
+                    const Vec<VPL> &Din, Vec<VPL> &Dout) {
+        Vec<VPL> w, n, e;
+        fetch(w, n, e, Dout);
+        if (y > g.vhi) {                       // block-uniform: the row below the image sends nothing
 #pragma unroll
-            for (int v = 0; v < VPL; ++v) Scur.q[v] = zero4();
+            for (int v = 0; v < VPL; ++v) Sin.q[v] = zero4();
         }
-        // S'(y+1, x) = norm(U_S(y, x))
-        Vec<VPL> Snext;
-#pragma unroll
-        for (int v = 0; v < VPL; ++v) Snext.q[v] = sum4(cur.w.q[v], cur.n.q[v], cur.e.q[v], cur.d.q[v]);
-        normalise<LPP, VPL, FULL>(Snext, ln);
-        if (STORE_S && st_n && y + 1 <= yb1) store_vec(Sout, y + 1, x, Snext);
         // W'(y, x-1) = norm(U_W(y, x))
         Vec<VPL> t;
 #pragma unroll
-        for (int v = 0; v < VPL; ++v) t.q[v] = sum4(Scur.q[v], cur.n.q[v], cur.e.q[v], cur.d.q[v]);
+        for (int v = 0; v < VPL; ++v) t.q[v] = sum4(Sin.q[v], n.q[v], e.q[v], Dout.q[v]);
         normalise<LPP, VPL, FULL>(t, ln);
 #pragma unroll
         for (int v = 0; v < VPL; ++v) ex(par, v, tid) = t.q[v];
-        if (st_w && y <= yb1) store_vec(Wout, y, x - 1, t);
-        __syncthreads();
+        mbar_arrive(xbar);
+        if (st_w && y <= yb1) store_at(Wout, row_off - (unsigned)g.Dp, t);
+        // S'(y+1, x) = norm(U_S(y, x))  -- independent of the exchange
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) Snext.q[v] = sum4(w.q[v], n.q[v], e.q[v], Dout.q[v]);
+        normalise<LPP, VPL, FULL>(Snext, ln);
+        if (STORE_S && st_n && y + 1 <= yb1) store_at(Sout, row_off + row_stride, Snext);
+        mbar_wait(xbar, xphase);
+        xphase ^= 1u;
         refill(y - yb0 + 1);
         // X = S'(y, x) + W'(y, x)
-        Vec<VPL> X;
 #pragma unroll
-        for (int v = 0; v < VPL; ++v) X.q[v] = add4(Scur.q[v], ex(par, v, rd_slot));
+        for (int v = 0; v < VPL; ++v) Xout.q[v] = add4(Sin.q[v], ex(par, v, rd_slot));
         // N'(y-1, x) = norm(U_N(y, x))
 #pragma unroll
-        for (int v = 0; v < VPL; ++v) t.q[v] = add4(add4(X.q[v], cur.e.q[v]), cur.d.q[v]);
+        for (int v = 0; v < VPL; ++v) t.q[v] = add4(add4(Xout.q[v], e.q[v]), Dout.q[v]);
         normalise<LPP, VPL, FULL>(t, ln);
-        const bool upper = (y > yb0);
-        if (upper && st_n) store_vec(Nout, y - 1, x, t);
+        const bool upper = (y > yb0);          // row y-1 belongs to this band
+        if (upper && st_n) store_at(Nout, row_off - row_stride, t);
         // E'(y-1, x+1) = norm(U_E(y-1, x))
 #pragma unroll
-        for (int v = 0; v < VPL; ++v) t.q[v] = add4(add4(Xprev.q[v], t.q[v]), Dprev.q[v]);
+        for (int v = 0; v < VPL; ++v) t.q[v] = add4(add4(Xin.q[v], t.q[v]), Din.q[v]);
         normalise<LPP, VPL, FULL>(t, ln);
-        if (upper && st_e) store_vec(Eout, y - 1, x + 1, t);
-        Xprev = X;
-        Dprev = cur.d;
-        Scur = Snext;
-        par ^= 1;
+        if (upper && st_e) store_at(Eout, row_off - row_stride + (unsigned)g.Dp, t);
+        row_off += row_stride;
+    };
+
+    for (int y = yb0;; y += 2) {
+        step(y, 0, S0, S1, X0, X1, D0, D1);
+        if (y == yb1 + 1) break;
+        step(y + 1, 1, S1, S0, X1, X0, D1, D0);
+        if (y == yb1) break;
     }
 }
 

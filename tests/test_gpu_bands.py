@@ -1,0 +1,55 @@
+"""Row-band mode of the CUDA matcher on ONE GPU: several band engines run in lock-step and swap
+their halo rows by device copies (what NCCL does between GPUs).  Must equal the un-banded CUDA
+result and the oracle bit for bit."""
+import numpy as np
+import pytest
+
+from oracle import mrf_c
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("world,shape,n_iter", [(2, (21, 50, 12), 5), (3, (20, 70, 32), 4), (4, (9, 33, 6), 6)])
+def test_cuda_band_engines_match_unbanded(hsm, world, shape, n_iter):
+    import torch
+    from importlib import import_module
+    bands = import_module("hybrid-stereo-matching_b200.bands")
+    synth = import_module("hybrid-stereo-matching_b200.synth")
+    rows, cols, levels = shape
+    left, right, disparity = synth.textured_pair(rows, cols, levels, 9, block=(5, 6))
+    prior = synth.sparse_prior(disparity, levels, 9, density=0.2)
+    kwargs = dict(prior_trust_factor=0.5, prior_influence_mode="const")
+
+    want = mrf_c.OracleMRFC((rows, cols), levels)
+    want_labels = want.lbp(left, right, prior, n_iter=n_iter, **kwargs)
+    single = hsm.StereoMRF((rows, cols), levels)
+    assert np.array_equal(single.lbp(left, right, prior, n_iter=n_iter, **kwargs), want_labels)
+
+    engines = [bands.CudaBandEngine(rows, cols, levels, *bands.band_bounds(rows, world, r)) for r in range(world)]
+    for e in engines:
+        with e.stream_context():
+            e.init_fields(left, right, prior, kwargs["prior_trust_factor"], kwargs["prior_influence_mode"])
+    tops = [e.new_halo() for e in engines]
+    bottoms = [e.new_halo() for e in engines]
+    for it in range(n_iter):
+        last = it == n_iter - 1
+        for e in engines:
+            with e.stream_context():
+                e.iterate(finalize=last)
+        if last:
+            break
+        for r, e in enumerate(engines):
+            with e.stream_context():
+                e.pack(tops[r] if r > 0 else None, bottoms[r] if r < world - 1 else None)
+        torch.cuda.synchronize()
+        for r, e in enumerate(engines):
+            with e.stream_context():
+                e.unpack(bottoms[r - 1] if r > 0 else None, tops[r + 1] if r < world - 1 else None)
+        torch.cuda.synchronize()
+    got = np.concatenate([e.labels() for e in engines], axis=0)
+    assert np.array_equal(got, want_labels)
+    want_planes = want._message_field
+    for r, e in enumerate(engines):
+        first, last_row = bands.band_bounds(rows, world, r)
+        for name, plane in e.planes().items():
+            assert np.array_equal(plane, want_planes[name][:, first:last_row + 1, :]), (r, name)
