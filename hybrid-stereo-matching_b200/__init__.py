@@ -7,5 +7,6 @@ The package directory is named after the project (``hybrid-stereo-matching_b200`
 """
 from ._capi import build_library, LIB_PATH      # noqa: F401
 from .mrf import StereoMRF, pinned_empty        # noqa: F401
+from .framed import FramebasedStereoMatching    # noqa: F401
 
-__all__ = ["StereoMRF", "pinned_empty", "build_library", "LIB_PATH"]
+__all__ = ["StereoMRF", "FramebasedStereoMatching", "pinned_empty", "build_library", "LIB_PATH"]

@@ -1,0 +1,97 @@
+"""The façade above the hot path (stereo_framebased.py:15-101 restated): prior selection by
+timestamp, call pattern, result stacking -- host logic tested on CPU with the oracle as the matcher;
+the GPU variant checks the batched CUDA path against the same sequence of oracle calls."""
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import mrf_numpy
+
+
+def _sequence(n=5, rows=14, cols=20, levels=6):
+    from importlib import import_module
+    synth = import_module("hybrid-stereo-matching_b200.synth")
+    lefts, rights, priors = synth.synthetic_sequence(n, rows, cols, levels, base_seed=50)
+    return lefts, rights, priors, np.arange(n) * 50.0 + 50.0
+
+
+def _reference_run(lefts, rights, ts, prior_info, levels):
+    """What the reference's run() computes, frame by frame (stereo_framebased.py:60-101)."""
+    out = []
+    matcher = mrf_numpy.OracleMRF(lefts.shape[1:], levels)
+    if prior_info is not None:
+        if len(prior_info["ts"]) > len(ts):
+            idx = [np.searchsorted(prior_info["ts"], t, side="left") for t in ts]
+            priors = prior_info["priors"][idx]
+        else:
+            priors = prior_info["priors"]
+        for l, r, p in zip(lefts, rights, priors):
+            out.append(matcher.lbp(l, r, p, prior_trust_factor=1.0, prior_influence_mode="adaptive", n_iter=10))
+    else:
+        for l, r in zip(lefts, rights):
+            out.append(matcher.lbp(l, r))
+    return np.asarray(out)
+
+
+def test_facade_host_logic_with_oracle_matcher(hsm):
+    lefts, rights, priors, ts = _sequence()
+    levels = 6
+    factory = lambda dim, lv: mrf_numpy.OracleMRF(dim, lv)
+    # more priors than frames: the closest later prior is picked
+    many_ts = np.arange(12) * 25.0
+    many = np.stack([np.roll(priors[i % len(priors)], i, axis=1) for i in range(12)])
+    info = {"ts": many_ts, "priors": many}
+    facade = hsm.FramebasedStereoMatching((20, 14), levels, inputs={"left": lefts, "right": rights, "ts": ts},
+                                          matcher_factory=factory)
+    assert facade.algorithm.dimension == (levels, 14, 20)        # (x, y) -> (rows, cols)
+    facade.run(info)
+    got = facade.get_output()
+    assert got.shape == (5, 14, 20)
+    assert np.array_equal(got, _reference_run(lefts, rights, ts, info, levels))
+    assert np.array_equal(facade.get_timestamps(), ts)
+    # same number of priors as frames, and no priors at all
+    for info in ({"ts": ts, "priors": priors}, None):
+        facade = hsm.FramebasedStereoMatching((20, 14), levels, inputs={"left": lefts, "right": rights, "ts": ts},
+                                              matcher_factory=factory)
+        facade.run(info)
+        assert np.array_equal(facade.get_output(), _reference_run(lefts, rights, ts, info, levels))
+    with pytest.raises(NotImplementedError):
+        hsm.FramebasedStereoMatching((20, 14), levels, algorithm="sgm")
+
+
+def test_shim_installs_reference_import_paths(hsm):
+    from importlib import import_module
+    shim = import_module("hybrid-stereo-matching_b200.shim")
+    saved = {k: v for k, v in sys.modules.items() if k.startswith("stereovis")}
+    try:
+        shim.install()
+        from stereovis.framed.algorithms import StereoMRF as A
+        from stereovis.framed.algorithms.mrf import StereoMRF as B
+        from stereovis.framed.stereo_framebased import FramebasedStereoMatching as F
+        assert A is hsm.StereoMRF and B is hsm.StereoMRF and F is hsm.FramebasedStereoMatching
+    finally:
+        for k in [k for k in sys.modules if k.startswith("stereovis")]:
+            del sys.modules[k]
+        sys.modules.update(saved)
+
+
+@pytest.mark.gpu
+def test_facade_batched_cuda_equals_sequential_reference(hsm):
+    lefts, rights, priors, ts = _sequence(n=7)
+    levels = 6
+    info = {"ts": ts, "priors": priors}
+    for capacity in (3, 16):
+        facade = hsm.FramebasedStereoMatching((20, 14), levels, inputs={"left": lefts, "right": rights, "ts": ts},
+                                              capacity=capacity)
+        facade.run(info)
+        assert np.array_equal(facade.get_output(), _reference_run(lefts, rights, ts, info, levels))
+    facade = hsm.FramebasedStereoMatching((20, 14), levels, inputs={"left": lefts, "right": rights, "ts": ts})
+    facade.run(None)
+    assert np.array_equal(facade.get_output(), _reference_run(lefts, rights, ts, None, levels))
+    # online call pattern: int32 shared-buffer prior with -1 fill, n_iter kwarg only (online_processing.py:121-128)
+    online = hsm.FramebasedStereoMatching((20, 14), levels)
+    prior32 = priors[0].astype(np.int32)
+    got = online.run_one_frame(lefts[0], rights[0], prior32, n_iter=4)
+    want = mrf_numpy.OracleMRF((14, 20), levels).lbp(lefts[0], rights[0], prior32, n_iter=4)
+    assert np.array_equal(got, want) and got.dtype == np.int64
