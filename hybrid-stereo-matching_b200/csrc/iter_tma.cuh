@@ -38,16 +38,21 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+#ifndef HSM_WAIT_HINT_NS
+#define HSM_WAIT_HINT_NS 20000
+#endif
+// try_wait suspends the thread in hardware until the phase completes or the time hint expires;
+// without a hint it returns after a short system limit and the retry loop burns issue slots.
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 {
     uint32_t done;
     do {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(done)
-            : "r"(smem_u32(bar)), "r"(parity)
+            : "r"(smem_u32(bar)), "r"(parity), "r"((uint32_t)HSM_WAIT_HINT_NS)
             : "memory");
     } while (!done);
 }
