@@ -97,6 +97,8 @@ def lib():
         "hsm_halo_unpack": ([vp, vp, vp], ci),
         "hsm_get_stats": ([vp, ctypes.POINTER(Stats)], ci),
         "hsm_reset_stats": ([vp], ci),
+        "hsm_rasterise_events": ([sz, vp, vp, vp, vp, ci, ci, ci, cd, vp, ci], ci),
+        "hsm_normalise_contrast": ([ci, ci, ci, vp, vp, ci], ci),
         "hsm_selftest_division": ([vp, vp, sz, ctypes.POINTER(ctypes.c_uint64)], ci),
         "hsm_host_alloc": ([sz, ctypes.POINTER(vp)], ci),
         "hsm_host_free": ([vp], ci),

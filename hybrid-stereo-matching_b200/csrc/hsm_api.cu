@@ -19,6 +19,7 @@
 
 #include "kernels.cuh"
 #include "iter_tma.cuh"
+#include "raster.cuh"
 
 using namespace hsm;
 
@@ -880,6 +881,59 @@ int hsm_reset_stats(hsm_matcher *m)
     const uint64_t bytes = m->stats.device_bytes;
     m->stats = hsm_stats{};
     m->stats.device_bytes = bytes;
+    return HSM_OK;
+}
+
+int hsm_rasterise_events(size_t n_events, const int *x, const int *y, const double *z, const int *frame,
+                         int n_frames, int rows, int cols, double fill, double *out, int device)
+{
+    if (n_frames < 0 || rows < 1 || cols < 1) return fail(HSM_ERR_ARG, "bad raster geometry");
+    if (!out || (n_events && (!x || !y || !z || !frame))) return fail(HSM_ERR_ARG, "null argument");
+    const size_t n_pixels = (size_t)n_frames * rows * cols;
+    if (n_pixels == 0) return HSM_OK;
+    if (n_events > 0x7fffffffull) return fail(HSM_ERR_ARG, "too many events");
+    CUDA_TRY(cudaSetDevice(device));
+    int *dx = nullptr, *dy = nullptr, *df = nullptr, *dw = nullptr;
+    double *dz = nullptr, *dout = nullptr;
+    CUDA_TRY(cudaMalloc((void **)&dw, n_pixels * sizeof(int)));
+    CUDA_TRY(cudaMalloc((void **)&dout, n_pixels * sizeof(double)));
+    CUDA_TRY(cudaMemset(dw, 0xff, n_pixels * sizeof(int)));          // -1: no event
+    if (n_events) {
+        CUDA_TRY(cudaMalloc((void **)&dx, n_events * sizeof(int)));
+        CUDA_TRY(cudaMalloc((void **)&dy, n_events * sizeof(int)));
+        CUDA_TRY(cudaMalloc((void **)&df, n_events * sizeof(int)));
+        CUDA_TRY(cudaMalloc((void **)&dz, n_events * sizeof(double)));
+        CUDA_TRY(cudaMemcpy(dx, x, n_events * sizeof(int), cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(dy, y, n_events * sizeof(int), cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(df, frame, n_events * sizeof(int), cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(dz, z, n_events * sizeof(double), cudaMemcpyHostToDevice));
+        const int blocks = (int)std::min<size_t>((n_events + 255) / 256, (size_t)148 * 16);
+        k_raster_winner<<<blocks, 256>>>(dx, dy, df, n_events, rows, cols, dw);
+        CUDA_TRY(cudaGetLastError());
+    }
+    const int blocks = (int)std::min<size_t>((n_pixels + 255) / 256, (size_t)148 * 16);
+    k_raster_gather<<<blocks, 256>>>(dw, dz, n_pixels, fill, dout);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpy(out, dout, n_pixels * sizeof(double), cudaMemcpyDeviceToHost));
+    cudaFree(dx); cudaFree(dy); cudaFree(df); cudaFree(dz); cudaFree(dw); cudaFree(dout);
+    return HSM_OK;
+}
+
+int hsm_normalise_contrast(int n_frames, int rows, int cols, const double *in, double *out, int device)
+{
+    if (n_frames < 0 || rows < 1 || cols < 1) return fail(HSM_ERR_ARG, "bad frame geometry");
+    if (n_frames == 0) return HSM_OK;
+    if (!in || !out) return fail(HSM_ERR_ARG, "null argument");
+    const size_t frame_elems = (size_t)rows * cols, bytes = (size_t)n_frames * frame_elems * sizeof(double);
+    CUDA_TRY(cudaSetDevice(device));
+    double *din = nullptr, *dout = nullptr;
+    CUDA_TRY(cudaMalloc((void **)&din, bytes));
+    CUDA_TRY(cudaMalloc((void **)&dout, bytes));
+    CUDA_TRY(cudaMemcpy(din, in, bytes, cudaMemcpyHostToDevice));
+    k_normalise_contrast<<<n_frames, 1024>>>(din, dout, frame_elems);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpy(out, dout, bytes, cudaMemcpyDeviceToHost));
+    cudaFree(din); cudaFree(dout);
     return HSM_OK;
 }
 

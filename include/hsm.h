@@ -161,6 +161,24 @@ int hsm_get_stats(hsm_matcher *m, hsm_stats *out);
 int hsm_reset_stats(hsm_matcher *m);
 
 /*
+ * Prior rasterisation (next row N2): replaces the scatter of generate_frames_from_spikes
+ * (stereovis/utils/frames_io.py:239-244).  Events are given in the order the reference would write
+ * them (frames_io.py:184-204 is done by the host): x, y pixel coordinates (already wrapped into
+ * [0, cols) / [0, rows)), z the value, frame the destination frame.  Later events overwrite earlier
+ * ones on the same pixel of the same frame; untouched pixels get `fill`.  out: n_frames x rows x cols
+ * float64 on the host.  All arrays are host arrays.
+ */
+int hsm_rasterise_events(size_t n_events, const int *x, const int *y, const double *z, const int *frame,
+                         int n_frames, int rows, int cols, double fill, double *out, int device);
+
+/*
+ * Frame pre-processing (next row N3): per-frame min-max contrast normalisation in float64, replaces
+ * normalise_contrast of stereovis/utils/frames_io.py:103-109 (used by load_frames(adjust_contrast=True),
+ * hybrid_stereo.py:90-103).  in/out: n_frames x rows x cols float64 host arrays (may alias).
+ */
+int hsm_normalise_contrast(int n_frames, int rows, int cols, const double *in, double *out, int device);
+
+/*
  * Self-test of the shared-reciprocal division used by the fused kernel: a4 holds n x 4
  * numerators, b holds n divisors (host arrays); *mismatches = how many of the 4n quotients
  * differ in bits from div.rn.f32 (must be 0).
