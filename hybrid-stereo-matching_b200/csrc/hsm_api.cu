@@ -19,6 +19,7 @@
 
 #include "kernels.cuh"
 #include "iter_tma.cuh"
+#include "iter2_tma.cuh"
 #include "raster.cuh"
 
 using namespace hsm;
@@ -465,6 +466,52 @@ int launch_tma(hsm_matcher *m, bool store_s)
     return HSM_OK;
 }
 
+// Two iterations per launch (algorithm 3).  Returns HSM_OK and sets *launched = false when the
+// configuration cannot use it (caller falls back to one iteration per launch).
+template <int LPP, int VPL, int NT>
+int launch_tma2(hsm_matcher *m, bool store_s, bool *launched)
+{
+    *launched = false;
+    constexpr int PX = NT / LPP, TX = PX - 4, SLOTS = NT + LPP;
+    if (TX < 4) return HSM_OK;
+    const size_t stage_bytes = StageLayout<LPP, VPL, NT>::stage_bytes(m->Dp, false);
+    const size_t fixed_bytes = Ring2Layout<LPP, VPL, NT>::ring_bytes(m->Dp) + (size_t)2 * VPL * SLOTS * 16 + 128;
+    int stages = m->stages > 0 ? m->stages : 3;
+    while (stages > 2 && fixed_bytes + stages * stage_bytes > (size_t)113 * 1024) --stages;
+    const size_t smem = fixed_bytes + (size_t)stages * stage_bytes;
+    if (smem > (size_t)227 * 1024) return HSM_OK;
+    HSM_TRY(ensure_maps(m));
+    const Geo g = geometry(m);
+    const int strips = (m->W + TX - 1) / TX;
+    IterArgs a;
+    a.Win = m->Wm[m->cur]; a.Nin = m->Nm[m->cur]; a.Ein = m->Em[m->cur];
+    a.Wout = m->Wm[m->cur ^ 1]; a.Nout = m->Nm[m->cur ^ 1]; a.Eout = m->Em[m->cur ^ 1];
+    a.Sout = m->S;
+    a.Dt = m->Dt; a.L = m->L; a.R = m->R; a.P = m->have_prior ? m->P : nullptr;
+    a.blend = m->blend;
+    a.olo = m->olo; a.ohi = m->ohi;
+    a.band_rows = choose_band_rows(m, strips);
+    a.store_s = store_s ? 1 : 0;
+    a.has_prior = m->have_prior ? 1 : 0;
+    const int bands = (m->ohi - m->olo + 1 + a.band_rows - 1) / a.band_rows;
+    dim3 grid(strips, bands, m->frames);
+    const bool full = (m->D == 4 * LPP * VPL);
+    const CUtensorMap &tw = m->tmW[m->cur], &tn = m->tmN[m->cur], &te = m->tmE[m->cur];
+#define HSM_LAUNCH_TMA2(F)                                                                                   \
+    do {                                                                                                     \
+        auto kernel = k_iter2_tma<LPP, VPL, NT, F>;                                                          \
+        CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
+        kernel<<<grid, NT, smem, m->stream>>>(tw, tn, te, m->tmI.L, m->tmI.R, m->tmI.P, g, a, stages);       \
+    } while (0)
+    if (full) HSM_LAUNCH_TMA2(true); else HSM_LAUNCH_TMA2(false);
+#undef HSM_LAUNCH_TMA2
+    HSM_TRY(check_launch(m, "k_iter2_tma"));
+    m->stats.iteration_launches++;
+    m->cur ^= 1;
+    *launched = true;
+    return HSM_OK;
+}
+
 int launch_directional(hsm_matcher *m)
 {
     const Geo g = geometry(m);
@@ -578,7 +625,7 @@ int hsm_set_option(hsm_matcher *m, int key, int value)
     if (!m) return fail(HSM_ERR_ARG, "null matcher");
     switch (key) {
         case HSM_OPT_ALGORITHM:
-            if (value < 0 || value > 2) return fail(HSM_ERR_ARG, "algorithm must be 0, 1 or 2");
+            if (value < 0 || value > 3) return fail(HSM_ERR_ARG, "algorithm must be 0, 1, 2 or 3");
             m->algorithm = value; return HSM_OK;
         case HSM_OPT_BAND_ROWS:
             if (value < 0) return fail(HSM_ERR_ARG, "band_rows must be >= 0");
@@ -692,13 +739,21 @@ int hsm_iterate(hsm_matcher *m, int n_iter, int finalize)
     for (int it = 0; it < n_iter; ++it) {
         if (m->algorithm == 0) {
             HSM_TRY(launch_directional(m));
-        } else {
-            const bool store_s = finalize && (it == n_iter - 1);
-            if (m->algorithm == 2 && tma_supported(m))
-                HSM_DISPATCH(m->cfg, { HSM_TRY((launch_tma<LPP, VPL, NT>(m, store_s))); });
-            else
-                HSM_DISPATCH(m->cfg, { HSM_TRY((launch_fused<LPP, VPL, NT>(m, store_s))); });
+            continue;
         }
+        const int left = n_iter - it;
+        // algorithm 3: pairs of iterations fused in one launch; an odd count starts with a single one
+        if (m->algorithm == 3 && tma_supported(m) && m->data_term == 1 && left >= 2 && left % 2 == 0) {
+            bool launched = false;
+            const bool store_s2 = finalize && left == 2;
+            HSM_DISPATCH(m->cfg, { HSM_TRY((launch_tma2<LPP, VPL, NT>(m, store_s2, &launched))); });
+            if (launched) { ++it; continue; }
+        }
+        const bool store_s = finalize && (it == n_iter - 1);
+        if (m->algorithm >= 2 && tma_supported(m))
+            HSM_DISPATCH(m->cfg, { HSM_TRY((launch_tma<LPP, VPL, NT>(m, store_s))); });
+        else
+            HSM_DISPATCH(m->cfg, { HSM_TRY((launch_fused<LPP, VPL, NT>(m, store_s))); });
     }
     CUDA_TRY(cudaEventRecord(ev.second, m->stream));
     m->pending.push_back(ev);

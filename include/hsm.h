@@ -54,7 +54,9 @@ extern "C" {
 
 /* hsm_set_option keys */
 #define HSM_OPT_ALGORITHM 0   /* 0 = one kernel per direction (T80), 1 = fused iteration fed by LDG,
-                                 2 = fused iteration fed by TMA (default; falls back to 1 if n_levels > 256) */
+                                 2 = fused iteration fed by TMA (falls back to 1 if n_levels > 256),
+                                 3 = two iterations per launch through a shared-memory row ring
+                                     (falls back to 2 for an odd leftover / unsupported shapes) */
 #define HSM_OPT_BAND_ROWS 1   /* rows per CTA band in the fused kernel; 0 = heuristic                */
 #define HSM_OPT_DATA_TERM 2   /* 0 = read the data plane (T28), 1 = recompute it in-kernel (T24, default) */
 #define HSM_OPT_VALID_LO 3    /* row-band mode: first/last local row that is inside the image ...    */
