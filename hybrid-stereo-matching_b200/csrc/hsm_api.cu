@@ -20,6 +20,7 @@
 #include "kernels.cuh"
 #include "iter_tma.cuh"
 #include "iter2_tma.cuh"
+#include "iter_ws.cuh"
 #include "raster.cuh"
 
 using namespace hsm;
@@ -340,6 +341,10 @@ int launch_fused(hsm_matcher *m, bool store_s)
     return HSM_OK;
 }
 
+#ifndef HSM_L2_PROMOTION
+#define HSM_L2_PROMOTION CU_TENSOR_MAP_L2_PROMOTION_L2_128B
+#endif
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -372,7 +377,7 @@ int make_plane_map(const hsm_matcher *m, CUtensorMap *map, float *plane, int px)
     const cuuint32_t estr[4] = {1, 1, 1, 1};
     float *base = plane + (size_t)m->vlo * m->W * m->Dp;
     CUresult rc = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, base, dims, strides, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, HSM_L2_PROMOTION,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (rc != CUDA_SUCCESS) return fail(HSM_ERR_CUDA, "cuTensorMapEncodeTiled failed with code %d", (int)rc);
     return HSM_OK;
@@ -512,6 +517,54 @@ int launch_tma2(hsm_matcher *m, bool store_s, bool *launched)
     return HSM_OK;
 }
 
+// Warp-specialised variant (algorithm 4): NT consumer threads + one producer warp.
+template <int LPP, int VPL, int NT>
+int launch_ws(hsm_matcher *m, bool store_s)
+{
+    HSM_TRY(ensure_maps(m));
+    const Geo g = geometry(m);
+    constexpr int PX = NT / LPP, TX = PX - 2, NW = NT / 32, XR = 4;
+    const int strips = (m->W + TX - 1) / TX;
+    IterArgs a;
+    a.Win = m->Wm[m->cur]; a.Nin = m->Nm[m->cur]; a.Ein = m->Em[m->cur];
+    a.Wout = m->Wm[m->cur ^ 1]; a.Nout = m->Nm[m->cur ^ 1]; a.Eout = m->Em[m->cur ^ 1];
+    a.Sout = m->S;
+    a.Dt = m->Dt; a.L = m->L; a.R = m->R; a.P = m->have_prior ? m->P : nullptr;
+    a.blend = m->blend;
+    a.olo = m->olo; a.ohi = m->ohi;
+    a.band_rows = choose_band_rows(m, strips);
+    a.store_s = store_s ? 1 : 0;
+    a.has_prior = m->have_prior ? 1 : 0;
+    const int bands = (m->ohi - m->olo + 1 + a.band_rows - 1) / a.band_rows;
+    dim3 grid(strips, bands, m->frames);
+    const bool dt_load = (m->data_term == 0);
+    const bool full = (m->D == 4 * LPP * VPL);
+    const size_t stage_bytes = StageLayout<LPP, VPL, NT>::stage_bytes(m->Dp, dt_load);
+    const size_t fixed_bytes = (size_t)NW * XR * VPL * LPP * 16 + (size_t)(2 * 3 + NW * XR) * 8 + 128;
+    int stages = m->stages > 0 ? std::min(m->stages, 3) : 3;      // the exchange ring holds stages + 1 rows
+    {
+        const int target_ctas = (NT == 256) ? (VPL == 1 ? 4 : 2) : (VPL == 1 ? 2 : 1);
+        const size_t budget = (size_t)227 * 1024 / target_ctas - 1024;
+        while (stages > 2 && fixed_bytes + stages * stage_bytes > budget) --stages;
+    }
+    const size_t smem = fixed_bytes + (size_t)stages * stage_bytes;
+    if (smem > (size_t)227 * 1024) return fail(HSM_ERR_ARG, "warp-specialised kernel needs %zu bytes of shared memory", smem);
+    const CUtensorMap &tw = m->tmW[m->cur], &tn = m->tmN[m->cur], &te = m->tmE[m->cur], &td = m->tmD;
+#define HSM_LAUNCH_WS(T, F)                                                                                  \
+    do {                                                                                                     \
+        auto kernel = k_iter_ws<LPP, VPL, NT, T, F>;                                                         \
+        CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
+        kernel<<<grid, NT + 32, smem, m->stream>>>(tw, tn, te, td, m->tmI.L, m->tmI.R, m->tmI.P, g, a, stages); \
+    } while (0)
+    if (full) { if (dt_load) HSM_LAUNCH_WS(true, true); else HSM_LAUNCH_WS(false, true); }
+    else { if (dt_load) HSM_LAUNCH_WS(true, false); else HSM_LAUNCH_WS(false, false); }
+#undef HSM_LAUNCH_WS
+    HSM_TRY(check_launch(m, "k_iter_ws"));
+    m->stats.iteration_launches++;
+    m->cur ^= 1;
+    return HSM_OK;
+}
+
 int launch_directional(hsm_matcher *m)
 {
     const Geo g = geometry(m);
@@ -625,7 +678,7 @@ int hsm_set_option(hsm_matcher *m, int key, int value)
     if (!m) return fail(HSM_ERR_ARG, "null matcher");
     switch (key) {
         case HSM_OPT_ALGORITHM:
-            if (value < 0 || value > 3) return fail(HSM_ERR_ARG, "algorithm must be 0, 1, 2 or 3");
+            if (value < 0 || value > 4) return fail(HSM_ERR_ARG, "algorithm must be 0..4");
             m->algorithm = value; return HSM_OK;
         case HSM_OPT_BAND_ROWS:
             if (value < 0) return fail(HSM_ERR_ARG, "band_rows must be >= 0");
@@ -750,7 +803,9 @@ int hsm_iterate(hsm_matcher *m, int n_iter, int finalize)
             if (launched) { ++it; continue; }
         }
         const bool store_s = finalize && (it == n_iter - 1);
-        if (m->algorithm >= 2 && tma_supported(m))
+        if (m->algorithm == 4 && tma_supported(m))
+            HSM_DISPATCH(m->cfg, { HSM_TRY((launch_ws<LPP, VPL, NT>(m, store_s))); });
+        else if (m->algorithm >= 2 && tma_supported(m))
             HSM_DISPATCH(m->cfg, { HSM_TRY((launch_tma<LPP, VPL, NT>(m, store_s))); });
         else
             HSM_DISPATCH(m->cfg, { HSM_TRY((launch_fused<LPP, VPL, NT>(m, store_s))); });
@@ -1010,6 +1065,16 @@ int hsm_selftest_division(const float *a4, const float *b, size_t n, unsigned lo
     cudaFree(da); cudaFree(db); cudaFree(dm);
     return HSM_OK;
 }
+
+#ifdef HSM_DEBUG_COUNT
+int hsm_debug_counters(unsigned long long *out8, int reset)
+{
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMemcpyFromSymbol(out8, hsm::g_dbg, 8 * sizeof(unsigned long long)));
+    if (reset) { unsigned long long z[8] = {0}; CUDA_TRY(cudaMemcpyToSymbol(hsm::g_dbg, z, sizeof z)); }
+    return HSM_OK;
+}
+#endif
 
 int hsm_host_alloc(size_t bytes, void **out)
 {

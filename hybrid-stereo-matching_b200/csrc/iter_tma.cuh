@@ -72,6 +72,12 @@ __device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *map, u
         : "memory");
 }
 
+#ifdef HSM_DEBUG_COUNT
+__device__ unsigned long long g_dbg[8];
+#define HSM_DBG(i) do { if ((threadIdx.x & 31) == 0) atomicAdd(&g_dbg[i], 1ull); } while (0)
+#else
+#define HSM_DBG(i) do { } while (0)
+#endif
 #ifndef HSM_TMA_MIN_BLOCKS
 #define HSM_TMA_MIN_BLOCKS 3
 #endif
@@ -200,7 +206,7 @@ __global__ void __launch_bounds__(NT, (NT == 256 && VPL == 1) ? HSM_TMA_MIN_BLOC
     const float4 *lane_base = reinterpret_cast<const float4 *>(smem_raw) + lane_f4;
     const unsigned char *img_base = smem_raw + planes_bytes;
     int stage = 0;
-    uint32_t phase = 0, xphase = 0;
+    uint32_t phase = 0;
     // element offset of (row y, this lane's pixel and chunk) inside the frame; advanced by one row per step
     // (x may be -1 or W for halo lanes: the wrap-around cancels when the neighbour offset is added)
     unsigned row_off = (unsigned)yb0 * row_stride + (unsigned)x * (unsigned)g.Dp + 4u * (unsigned)ln.c;
@@ -266,36 +272,77 @@ __global__ void __launch_bounds__(NT, (NT == 256 && VPL == 1) ? HSM_TMA_MIN_BLOC
 #pragma unroll
             for (int v = 0; v < VPL; ++v) Sin.q[v] = zero4();
         }
-        // W'(y, x-1) = norm(U_W(y, x))
+        // W'(y, x-1) = norm(U_W(y, x)) and S'(y+1, x) = norm(U_S(y, x)): independent of each other,
+        // normalised branch-free; one warp-uniform fallback if any lane saw an out-of-range operand.
         Vec<VPL> t;
 #pragma unroll
-        for (int v = 0; v < VPL; ++v) t.q[v] = sum4(Sin.q[v], n.q[v], e.q[v], Dout.q[v]);
-        normalise<LPP, VPL, FULL>(t, ln);
+        for (int v = 0; v < VPL; ++v) {
+            t.q[v] = sum4(Sin.q[v], n.q[v], e.q[v], Dout.q[v]);
+            Snext.q[v] = sum4(w.q[v], n.q[v], e.q[v], Dout.q[v]);
+        }
+        bool mok_w, mok_s;
+        bool bad = normalise_fast<LPP, VPL, FULL>(t, ln, &mok_w);
+        bad |= normalise_fast<LPP, VPL, FULL>(Snext, ln, &mok_s);
+        HSM_DBG(0);
+        if (__any_sync(0xffffffffu, bad)) {                        // warp-uniform, uncommon
+            HSM_DBG(1);
+            Vec<VPL> uw, us;
+#pragma unroll
+            for (int v = 0; v < VPL; ++v) {
+                uw.q[v] = sum4(Sin.q[v], n.q[v], e.q[v], Dout.q[v]);
+                us.q[v] = sum4(w.q[v], n.q[v], e.q[v], Dout.q[v]);
+            }
+            // zeros (border columns, halo lanes) are fine for the fast path; anything else is redone exactly
+            const bool exact = lane_needs_exact<LPP, VPL, FULL>(uw, ln, mok_w) ||
+                               lane_needs_exact<LPP, VPL, FULL>(us, ln, mok_s);
+            if (__any_sync(0xffffffffu, exact)) {
+                HSM_DBG(3);
+                normalise<LPP, VPL, FULL>(uw, ln);
+                normalise<LPP, VPL, FULL>(us, ln);
+                t = uw;
+                Snext = us;
+            }
+        }
 #pragma unroll
         for (int v = 0; v < VPL; ++v) ex(par, v, tid) = t.q[v];
-        mbar_arrive(xbar);
         if (st_w && y <= yb1) store_at(Wout, row_off - (unsigned)g.Dp, t);
-        // S'(y+1, x) = norm(U_S(y, x))  -- independent of the exchange
-#pragma unroll
-        for (int v = 0; v < VPL; ++v) Snext.q[v] = sum4(w.q[v], n.q[v], e.q[v], Dout.q[v]);
-        normalise<LPP, VPL, FULL>(Snext, ln);
         if (STORE_S && st_n && y + 1 <= yb1) store_at(Sout, row_off + row_stride, Snext);
-        mbar_wait(xbar, xphase);
-        xphase ^= 1u;
+        __syncthreads();                       // the row's only CTA barrier: W' published, stage consumed
         refill(y - yb0 + 1);
         // X = S'(y, x) + W'(y, x)
 #pragma unroll
         for (int v = 0; v < VPL; ++v) Xout.q[v] = add4(Sin.q[v], ex(par, v, rd_slot));
-        // N'(y-1, x) = norm(U_N(y, x))
+        // N'(y-1, x) = norm(U_N(y, x));  E'(y-1, x+1) = norm(U_E(y-1, x)) needs N'(y-1, x)
+        Vec<VPL> tn;
 #pragma unroll
-        for (int v = 0; v < VPL; ++v) t.q[v] = add4(add4(Xout.q[v], e.q[v]), Dout.q[v]);
-        normalise<LPP, VPL, FULL>(t, ln);
+        for (int v = 0; v < VPL; ++v) tn.q[v] = add4(add4(Xout.q[v], e.q[v]), Dout.q[v]);
+        bool mok_n, mok_e;
+        bad = normalise_fast<LPP, VPL, FULL>(tn, ln, &mok_n);
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) t.q[v] = add4(add4(Xin.q[v], tn.q[v]), Din.q[v]);
+        bad |= normalise_fast<LPP, VPL, FULL>(t, ln, &mok_e);
+        if (__any_sync(0xffffffffu, bad)) {
+            HSM_DBG(2);
+            Vec<VPL> un, ue;
+#pragma unroll
+            for (int v = 0; v < VPL; ++v) un.q[v] = add4(add4(Xout.q[v], e.q[v]), Dout.q[v]);
+            bool exact = lane_needs_exact<LPP, VPL, FULL>(un, ln, mok_n);
+            // U_E is built from the (fast) N'; if that one is kept, so is the sum
+#pragma unroll
+            for (int v = 0; v < VPL; ++v) ue.q[v] = add4(add4(Xin.q[v], tn.q[v]), Din.q[v]);
+            exact = exact || lane_needs_exact<LPP, VPL, FULL>(ue, ln, mok_e);
+            if (__any_sync(0xffffffffu, exact)) {
+                HSM_DBG(4);
+                normalise<LPP, VPL, FULL>(un, ln);
+                tn = un;
+#pragma unroll
+                for (int v = 0; v < VPL; ++v) ue.q[v] = add4(add4(Xin.q[v], tn.q[v]), Din.q[v]);
+                normalise<LPP, VPL, FULL>(ue, ln);
+                t = ue;
+            }
+        }
         const bool upper = (y > yb0);          // row y-1 belongs to this band
-        if (upper && st_n) store_at(Nout, row_off - row_stride, t);
-        // E'(y-1, x+1) = norm(U_E(y-1, x))
-#pragma unroll
-        for (int v = 0; v < VPL; ++v) t.q[v] = add4(add4(Xin.q[v], t.q[v]), Din.q[v]);
-        normalise<LPP, VPL, FULL>(t, ln);
+        if (upper && st_n) store_at(Nout, row_off - row_stride, tn);
         if (upper && st_e) store_at(Eout, row_off - row_stride + (unsigned)g.Dp, t);
         row_off += row_stride;
     };

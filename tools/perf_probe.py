@@ -27,7 +27,7 @@ def run(rows, cols, levels, batch, n_iter, algorithm, data_term, band_rows, stag
     m.set_option(capi.OPT_BAND_ROWS, band_rows)
     m.set_option(capi.OPT_STAGES, stages)
     m._init_fields(lefts, rights, priors, 1.0, "adaptive", True, _batched=True)
-    capi.check(capi.lib().hsm_iterate(m._handle, 3, 1))
+    capi.check(capi.lib().hsm_iterate(m._handle, int(os.environ.get("HSM_WARM", "3")), 1))
     m.synchronize()
     m.reset_stats()
     capi.check(capi.lib().hsm_iterate(m._handle, n_iter, 1))
