@@ -86,7 +86,7 @@ bool lane_cfg(int D, LaneCfg *c)
     if (D <= 16) pick = 0;
     else if (D <= 32) pick = 1;
     else if (D <= 64) pick = 7;        // 8 lanes x 2 float4: measured faster than 16 x 1 at 640x480xD64
-    else if (D <= 128) pick = 3;
+    else if (D <= 128) pick = 8;       // 16 lanes x 2 float4: measured faster than 32 x 1 at 480x270xD128
     else if (D <= 256) pick = 4;
     else if (D <= 512) pick = 5;
     else return false;
