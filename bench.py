@@ -296,7 +296,7 @@ def main():
                     "d2h_bytes_per_step": int(h_out.nbytes), "timing": "wall clock between device synchronisations",
                     "labels_equal_device_arm": same},
             "gpu_launches": int(stats["kernel_launches"]),
-            "roofline": {"bound": "hbm", "kernel": "k_iter_tma (fused 4-sweep BP iteration)",
+            "roofline": {"bound": "hbm", "kernel": "k_iter_tmast (fused 4-sweep BP iteration, TMA loads + TMA stores)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "peak_source": peak_source, "algorithmic_bytes_per_launch": algo_bytes,
                          "launch_ms": launch_ms, "launches_timed": int(launches),

@@ -21,6 +21,7 @@
 #include "iter_tma.cuh"
 #include "iter2_tma.cuh"
 #include "iter_ws.cuh"
+#include "iter_tma_st.cuh"
 #include "raster.cuh"
 
 using namespace hsm;
@@ -132,9 +133,10 @@ struct hsm_matcher {
     bool have_fields = false, have_prior = false, dt_valid = false, s_valid = true;
     Blend blend{kPriorNone, 0.0f, 0.0};
     // options
-    int algorithm = 2, band_rows = 0, data_term = 1, stages = 0, lane_config = 0;
+    int algorithm = 5, band_rows = 0, data_term = 1, stages = 0, lane_config = 0;
     // TMA descriptors of the double-buffered planes (algorithm 2)
     CUtensorMap tmW[2], tmN[2], tmE[2], tmD;
+    CUtensorMap tsW[2], tsN[2], tsE[2];          // store maps (box = TX output pixels)
     ImageMaps tmI;
     bool maps_valid = false;
     int vlo = 0, vhi = 0, olo = 0, ohi = 0;
@@ -412,6 +414,11 @@ int ensure_maps(hsm_matcher *m)
         HSM_TRY(make_plane_map(m, &m->tmE[i], m->Em[i], px));
     }
     HSM_TRY(make_plane_map(m, &m->tmD, m->Dt, px));
+    for (int i = 0; i < 2; ++i) {
+        HSM_TRY(make_plane_map(m, &m->tsW[i], m->Wm[i], px - 2));
+        HSM_TRY(make_plane_map(m, &m->tsN[i], m->Nm[i], px - 2));
+        HSM_TRY(make_plane_map(m, &m->tsE[i], m->Em[i], px - 2));
+    }
     // image segments: see StageLayout in iter_tma.cuh (LBOX, RSEG, RBOX)
     const int dcov = 4 * m->cfg.lpp * m->cfg.vpl, rseg = px + dcov + 4;
     const int rbox = rseg <= 256 ? rseg : ((rseg / 2 + 31) / 32 * 32);
@@ -565,6 +572,59 @@ int launch_ws(hsm_matcher *m, bool store_s)
     return HSM_OK;
 }
 
+// TMA-load + TMA-store variant (algorithm 5).  *launched = false if its shared memory does not fit.
+template <int LPP, int VPL, int NT>
+int launch_tmast(hsm_matcher *m, bool store_s, bool *launched)
+{
+    *launched = false;
+    constexpr int PX = NT / LPP, TX = PX - 2, SLOTS = NT + 2 * LPP;
+    const bool dt_load = (m->data_term == 0);
+    const size_t stage_bytes = StageLayout<LPP, VPL, NT>::stage_bytes(m->Dp, dt_load);
+    const size_t ost_bytes = ((size_t)TX * m->Dp * 4 + 127) & ~(size_t)127;
+    const size_t fixed_bytes = 6 * ost_bytes + (size_t)2 * VPL * SLOTS * 16 + 128;
+    int stages = m->stages;
+    if (stages <= 0) {
+        const int target_ctas = (NT == 256) ? (VPL == 1 ? 3 : 2) : (VPL == 1 ? 2 : 1);
+        const size_t budget = (size_t)227 * 1024 / target_ctas - 1024;
+        stages = 3;
+        while (stages > 2 && fixed_bytes + stages * stage_bytes > budget) --stages;
+    }
+    const size_t smem = fixed_bytes + (size_t)stages * stage_bytes;
+    if (smem > (size_t)227 * 1024) return HSM_OK;
+    HSM_TRY(ensure_maps(m));
+    const Geo g = geometry(m);
+    const int strips = (m->W + TX - 1) / TX;
+    IterArgs a;
+    a.Win = m->Wm[m->cur]; a.Nin = m->Nm[m->cur]; a.Ein = m->Em[m->cur];
+    a.Wout = m->Wm[m->cur ^ 1]; a.Nout = m->Nm[m->cur ^ 1]; a.Eout = m->Em[m->cur ^ 1];
+    a.Sout = m->S;
+    a.Dt = m->Dt; a.L = m->L; a.R = m->R; a.P = m->have_prior ? m->P : nullptr;
+    a.blend = m->blend;
+    a.olo = m->olo; a.ohi = m->ohi;
+    a.band_rows = choose_band_rows(m, strips);
+    a.store_s = store_s ? 1 : 0;
+    a.has_prior = m->have_prior ? 1 : 0;
+    const int bands = (m->ohi - m->olo + 1 + a.band_rows - 1) / a.band_rows;
+    dim3 grid(strips, bands, m->frames);
+    const bool full = (m->D == 4 * LPP * VPL);
+    const int in = m->cur, out = m->cur ^ 1;
+#define HSM_LAUNCH_TMAST(T, F)                                                                               \
+    do {                                                                                                     \
+        auto kernel = k_iter_tmast<LPP, VPL, NT, T, F>;                                                      \
+        CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
+        kernel<<<grid, NT, smem, m->stream>>>(m->tmW[in], m->tmN[in], m->tmE[in], m->tmD, m->tmI.L, m->tmI.R, \
+                                              m->tmI.P, m->tsW[out], m->tsN[out], m->tsE[out], g, a, stages);  \
+    } while (0)
+    if (full) { if (dt_load) HSM_LAUNCH_TMAST(true, true); else HSM_LAUNCH_TMAST(false, true); }
+    else { if (dt_load) HSM_LAUNCH_TMAST(true, false); else HSM_LAUNCH_TMAST(false, false); }
+#undef HSM_LAUNCH_TMAST
+    HSM_TRY(check_launch(m, "k_iter_tmast"));
+    m->stats.iteration_launches++;
+    m->cur ^= 1;
+    *launched = true;
+    return HSM_OK;
+}
+
 int launch_directional(hsm_matcher *m)
 {
     const Geo g = geometry(m);
@@ -678,7 +738,7 @@ int hsm_set_option(hsm_matcher *m, int key, int value)
     if (!m) return fail(HSM_ERR_ARG, "null matcher");
     switch (key) {
         case HSM_OPT_ALGORITHM:
-            if (value < 0 || value > 4) return fail(HSM_ERR_ARG, "algorithm must be 0..4");
+            if (value < 0 || value > 5) return fail(HSM_ERR_ARG, "algorithm must be 0..5");
             m->algorithm = value; return HSM_OK;
         case HSM_OPT_BAND_ROWS:
             if (value < 0) return fail(HSM_ERR_ARG, "band_rows must be >= 0");
@@ -803,6 +863,11 @@ int hsm_iterate(hsm_matcher *m, int n_iter, int finalize)
             if (launched) { ++it; continue; }
         }
         const bool store_s = finalize && (it == n_iter - 1);
+        if (m->algorithm == 5 && tma_supported(m)) {
+            bool launched = false;
+            HSM_DISPATCH(m->cfg, { HSM_TRY((launch_tmast<LPP, VPL, NT>(m, store_s, &launched))); });
+            if (launched) continue;
+        }
         if (m->algorithm == 4 && tma_supported(m))
             HSM_DISPATCH(m->cfg, { HSM_TRY((launch_ws<LPP, VPL, NT>(m, store_s))); });
         else if (m->algorithm >= 2 && tma_supported(m))

@@ -1,0 +1,308 @@
+// k_iter_tma with TMA STORES (algorithm 5): results are staged in shared memory and leave the SM
+// as one cp.async.bulk.tensor store per plane-row (issued by thread 0 after the row's barrier)
+// instead of per-thread STG.128 with 64-bit address arithmetic and edge predicates.  The TMA unit
+// clips columns >= W.  Everything else (arithmetic, pipeline, barrier) is k_iter_tma's.
+#pragma once
+
+#include "iter_tma.cuh"
+
+namespace hsm {
+
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap *map, const void *src, int c0, int c1, int c2, int c3)
+{
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                 ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_fence() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+template <int LPP, int VPL, int NT, bool DT_LOAD, bool FULL>
+__global__ void __launch_bounds__(NT, (NT == 256 && VPL == 1) ? HSM_TMA_MIN_BLOCKS : 1)
+    k_iter_tmast(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmN,
+               const __grid_constant__ CUtensorMap tmE, const __grid_constant__ CUtensorMap tmD,
+               const __grid_constant__ CUtensorMap tmL, const __grid_constant__ CUtensorMap tmR,
+               const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUtensorMap tsW,
+               const __grid_constant__ CUtensorMap tsN, const __grid_constant__ CUtensorMap tsE, Geo g, IterArgs a,
+               int stages)
+{
+    using SL = StageLayout<LPP, VPL, NT>;
+    const bool STORE_S = a.store_s != 0;
+    constexpr int PX = NT / LPP;
+    constexpr int TX = PX - 2;
+    constexpr int SLOTS = NT + 2 * LPP;
+    constexpr int NPL = DT_LOAD ? 4 : 3;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+
+    const int tid = threadIdx.x;
+    const int px = tid / LPP;
+    Lane<LPP, VPL> ln;
+    ln.init(tid % LPP, g.D, g.Dp);
+
+    const unsigned row_floats = (unsigned)PX * (unsigned)g.Dp;          // one plane's row segment
+    const unsigned stage_bytes = SL::stage_bytes(g.Dp, DT_LOAD);
+    const unsigned planes_bytes = SL::planes_bytes(g.Dp, DT_LOAD);
+    // output staging for the TMA stores: [plane W, N, E][2 buffers] of TX pixels, 128-byte aligned
+    const unsigned ost_bytes = (((unsigned)TX * (unsigned)g.Dp * 4u) + 127u) & ~127u;
+    unsigned char *ost = smem_raw + (size_t)stages * stage_bytes;
+    float4 *exch = reinterpret_cast<float4 *>(ost + 6u * ost_bytes);
+    uint64_t *full = reinterpret_cast<uint64_t *>(exch + 2 * VPL * SLOTS);
+    uint64_t *xbar = full + stages;                                      // W' exchange barrier (all NT threads)
+    auto ex = [&](int par, int v, int slot) -> float4 & { return exch[(par * VPL + v) * SLOTS + slot]; };
+
+    const int xs0 = (int)blockIdx.x * TX;
+    const int shift_l = (xs0 - 1) & 3, shift_r = (xs0 - SL::DCOV) & 3;    // see StageLayout
+    const int x = xs0 - 1 + px;
+    const bool in_x = (x >= 0 && x < g.W);
+    const int yb0 = a.olo + (int)blockIdx.y * a.band_rows;
+    const int yb1 = min(yb0 + a.band_rows - 1, a.ohi);
+    const int frame = (int)blockIdx.z;
+    const size_t fplane = (size_t)frame * g.plane_stride;
+    const unsigned row_stride = (unsigned)g.W * (unsigned)g.Dp;
+    const int n_rows = yb1 - yb0 + 3;                                    // rows yb0-1 .. yb1+1
+
+    const bool st_w = px >= 2;                                 // W'(y, x-1)  -> staging slot px-2
+    const bool st_n = px >= 1 && px <= PX - 2;                 // N'(y-1, x)  -> staging slot px-1   (and S')
+    const bool st_e = px <= PX - 3;                            // E'(y-1, x+1)-> staging slot px
+    const bool st_s = in_x && px >= 1 && px <= PX - 2;         // S' goes out with plain stores (last iteration only)
+    const int rd_slot = (x < 0) ? (NT + LPP + ln.c) : (tid + LPP);
+
+    if (tid == 0) {
+        for (int s = 0; s < stages; ++s) mbar_init(&full[s], 1);
+        mbar_init(xbar, NT);
+        mbar_fence_init();
+    }
+    if (tid < 2 * LPP) {
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) ex(0, v, NT + tid) = ex(1, v, NT + tid) = zero4();
+    }
+    __syncthreads();
+
+    // producer side (thread 0): one bulk tensor copy per plane into stage s for row index r
+    auto issue = [&](int r, int s) {
+        const int yy = yb0 - 1 + r - g.vlo;            // row coordinate inside the valid-row tensor
+        unsigned char *stage_ptr = smem_raw + (size_t)s * stage_bytes;
+        float *dst = reinterpret_cast<float *>(stage_ptr);
+        unsigned tx = NPL * row_floats * 4u;
+        if (!DT_LOAD) tx += SL::LBOX * 4u + SL::NRB * SL::RBOX * 4u + (a.has_prior ? SL::LBOX * 4u : 0u);
+        mbar_expect_tx(&full[s], tx);
+        tma_load_4d(dst, &tmW, &full[s], 0, xs0 - 1, yy, frame);
+        tma_load_4d(dst + row_floats, &tmN, &full[s], 0, xs0 - 1, yy, frame);
+        tma_load_4d(dst + 2 * row_floats, &tmE, &full[s], 0, xs0 - 1, yy, frame);
+        if (DT_LOAD) {
+            tma_load_4d(dst + 3 * row_floats, &tmD, &full[s], 0, xs0 - 1, yy, frame);
+        } else {
+            unsigned char *img = stage_ptr + planes_bytes;
+            tma_load_3d(img, &tmL, &full[s], xs0 - 1 - shift_l, yy, frame);
+#pragma unroll
+            for (int b = 0; b < SL::NRB; ++b)
+                tma_load_3d(img + SL::L_BYTES + b * SL::RBOX * 4, &tmR, &full[s],
+                            xs0 - SL::DCOV - shift_r + b * SL::RBOX, yy, frame);
+            if (a.has_prior) tma_load_3d(img + SL::L_BYTES + SL::R_BYTES, &tmP, &full[s], xs0 - 1 - shift_l, yy, frame);
+        }
+    };
+    if (tid == 0) {
+        const int first = n_rows < stages ? n_rows : stages;
+        for (int s = 0; s < first; ++s) issue(s, s);
+    }
+
+    float *Sout = a.Sout + fplane;
+    // this lane's float4 slot inside a staging buffer (pixel slot 0 <-> column xs0)
+    float4 *st_wp = reinterpret_cast<float4 *>(ost) + (px - 2) * (g.Dp / 4) + ln.c;
+    float4 *st_np = reinterpret_cast<float4 *>(ost + 2u * ost_bytes) + (px - 1) * (g.Dp / 4) + ln.c;
+    float4 *st_ep = reinterpret_cast<float4 *>(ost + 4u * ost_bytes) + px * (g.Dp / 4) + ln.c;
+    const unsigned ost_f4 = ost_bytes / 16u;
+    auto stage_out = [&](float4 *slot, int buf, const Vec<VPL> &val) {
+#pragma unroll
+        for (int v = 0; v < VPL; ++v)
+            if (FULL || ln.active[v]) slot[buf * ost_f4 + v * LPP] = val.q[v];
+    };
+    // thread 0: one bulk tensor store per plane-row; out-of-image columns are clipped by the TMA unit
+    auto tma_store_row = [&](const CUtensorMap *map, int plane, int buf, int y) {
+        tma_store_4d(map, ost + (2u * plane + buf) * ost_bytes, 0, xs0, y - g.vlo, frame);
+    };
+
+    // ---- consumer side ------------------------------------------------------------------------
+    // Carried between rows (two copies each, alternating per row so that no register moves are
+    // needed): S'(y, x), X(y-1, x) = S'(y-1, x) + W'(y-1, x), data term of row y-1.
+    Vec<VPL> S0, S1, X0, X1, D0, D1;
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) S0.q[v] = S1.q[v] = X0.q[v] = X1.q[v] = D0.q[v] = D1.q[v] = zero4();
+
+    const unsigned lane_f4 = (unsigned)px * (unsigned)(g.Dp / 4) + (unsigned)ln.c;   // float4 index in a row segment
+    const unsigned plane_f4 = row_floats / 4;
+    const float4 *lane_base = reinterpret_cast<const float4 *>(smem_raw) + lane_f4;
+    const unsigned char *img_base = smem_raw + planes_bytes;
+    int stage = 0;
+    uint32_t phase = 0;
+    // element offset of (row y, this lane's pixel and chunk) inside the frame; advanced by one row per step
+    // (x may be -1 or W for halo lanes: the wrap-around cancels when the neighbour offset is added)
+    unsigned row_off = (unsigned)yb0 * row_stride + (unsigned)x * (unsigned)g.Dp + 4u * (unsigned)ln.c;
+
+    // wait for the stage holding row y, copy this lane's chunks to registers, build the data term
+    auto fetch = [&](Vec<VPL> &w, Vec<VPL> &n, Vec<VPL> &e, Vec<VPL> &d) {
+        mbar_wait(&full[stage], phase);
+        const unsigned stage_off = (unsigned)stage * stage_bytes;
+        const float4 *sp = reinterpret_cast<const float4 *>(reinterpret_cast<const unsigned char *>(lane_base) + stage_off);
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) {
+            if (FULL || ln.active[v]) {
+                w.q[v] = sp[v * LPP];
+                n.q[v] = sp[plane_f4 + v * LPP];
+                e.q[v] = sp[2 * plane_f4 + v * LPP];
+                if (DT_LOAD) d.q[v] = sp[3 * plane_f4 + v * LPP];
+            } else {
+                w.q[v] = n.q[v] = e.q[v] = zero4();
+                if (DT_LOAD) d.q[v] = zero4();
+            }
+        }
+        if (!DT_LOAD) {
+            const unsigned char *img = img_base + stage_off;
+            data_vec_smem<LPP, VPL, FULL>(d, ln, reinterpret_cast<const float *>(img) + shift_l,
+                                          reinterpret_cast<const float *>(img + SL::L_BYTES) + shift_r,
+                                          reinterpret_cast<const int *>(img + SL::L_BYTES + SL::R_BYTES) + shift_l, px,
+                                          x, in_x, g.D, a.blend, a.has_prior != 0);
+        }
+    };
+    // every thread has copied the current stage: refill it with row index r + stages
+    auto refill = [&](int r) {
+        if (tid == 0 && r + stages < n_rows) issue(r + stages, stage);
+        if (++stage == stages) { stage = 0; phase ^= 1u; }
+    };
+    auto store_at = [&](float *plane, unsigned off, const Vec<VPL> &val) {
+#pragma unroll
+        for (int v = 0; v < VPL; ++v)
+            if (FULL || ln.active[v]) st_plain(plane + off + 4 * LPP * v, val.q[v]);
+    };
+
+    // row yb0-1 only contributes S'(yb0)
+    {
+        Vec<VPL> w, n, e, d;
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) d.q[v] = zero4();
+        fetch(w, n, e, d);
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) S0.q[v] = sum4(w.q[v], n.q[v], e.q[v], d.q[v]);
+        normalise<LPP, VPL, FULL>(S0, ln);
+        if (STORE_S && st_s) store_at(Sout, row_off, S0);
+        __syncthreads();
+        refill(0);
+    }
+
+    // One row: Sin = S'(y, x); Xin, Din belong to row y-1; Sout_/Xout/Dout are produced for the next row.
+    // The exchange of W' uses a split barrier: arrive after publishing W'(y, x-1), compute S'(y+1)
+    // (which does not depend on the neighbour), then wait and pick up W'(y, x).
+    auto step = [&](int y, const int par, Vec<VPL> &Sin, Vec<VPL> &Snext, const Vec<VPL> &Xin, Vec<VPL> &Xout,
+                    const Vec<VPL> &Din, Vec<VPL> &Dout) {
+        Vec<VPL> w, n, e;
+        fetch(w, n, e, Dout);
+        if (y > g.vhi) {                       // block-uniform: the row below the image sends nothing
+#pragma unroll
+            for (int v = 0; v < VPL; ++v) Sin.q[v] = zero4();
+        }
+        // W'(y, x-1) = norm(U_W(y, x)) and S'(y+1, x) = norm(U_S(y, x)): independent of each other,
+        // normalised branch-free; one warp-uniform fallback if any lane saw an out-of-range operand.
+        Vec<VPL> t;
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) {
+            t.q[v] = sum4(Sin.q[v], n.q[v], e.q[v], Dout.q[v]);
+            Snext.q[v] = sum4(w.q[v], n.q[v], e.q[v], Dout.q[v]);
+        }
+        bool mok_w, mok_s;
+        bool bad = normalise_fast<LPP, VPL, FULL>(t, ln, &mok_w);
+        bad |= normalise_fast<LPP, VPL, FULL>(Snext, ln, &mok_s);
+        HSM_DBG(0);
+        if (__any_sync(0xffffffffu, bad)) {                        // warp-uniform, uncommon
+            HSM_DBG(1);
+            Vec<VPL> uw, us;
+#pragma unroll
+            for (int v = 0; v < VPL; ++v) {
+                uw.q[v] = sum4(Sin.q[v], n.q[v], e.q[v], Dout.q[v]);
+                us.q[v] = sum4(w.q[v], n.q[v], e.q[v], Dout.q[v]);
+            }
+            // zeros (border columns, halo lanes) are fine for the fast path; anything else is redone exactly
+            const bool exact = lane_needs_exact<LPP, VPL, FULL>(uw, ln, mok_w) ||
+                               lane_needs_exact<LPP, VPL, FULL>(us, ln, mok_s);
+            if (__any_sync(0xffffffffu, exact)) {
+                HSM_DBG(3);
+                normalise<LPP, VPL, FULL>(uw, ln);
+                normalise<LPP, VPL, FULL>(us, ln);
+                t = uw;
+                Snext = us;
+            }
+        }
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) ex(par, v, tid) = t.q[v];
+        if (st_w) stage_out(st_wp, par, t);
+        if (STORE_S && st_s && y + 1 <= yb1) store_at(Sout, row_off + row_stride, Snext);
+        // staging writes (this row's W', the previous row's N', E') -> visible to the async proxy
+        tma_store_fence();
+        if (tid == 0) tma_store_wait_read();   // the buffers about to be reused have been read by the TMA unit
+        __syncthreads();                       // the row's only CTA barrier: W' published, stage consumed
+        refill(y - yb0 + 1);
+        if (tid == 0) {
+            if (y <= yb1) tma_store_row(&tsW, 0, par, y);
+            if (y > yb0 + 1) { tma_store_row(&tsN, 1, par ^ 1, y - 2); tma_store_row(&tsE, 2, par ^ 1, y - 2); }
+            tma_store_commit();
+        }
+        // X = S'(y, x) + W'(y, x)
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) Xout.q[v] = add4(Sin.q[v], ex(par, v, rd_slot));
+        // N'(y-1, x) = norm(U_N(y, x));  E'(y-1, x+1) = norm(U_E(y-1, x)) needs N'(y-1, x)
+        Vec<VPL> tn;
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) tn.q[v] = add4(add4(Xout.q[v], e.q[v]), Dout.q[v]);
+        bool mok_n, mok_e;
+        bad = normalise_fast<LPP, VPL, FULL>(tn, ln, &mok_n);
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) t.q[v] = add4(add4(Xin.q[v], tn.q[v]), Din.q[v]);
+        bad |= normalise_fast<LPP, VPL, FULL>(t, ln, &mok_e);
+        if (__any_sync(0xffffffffu, bad)) {
+            HSM_DBG(2);
+            Vec<VPL> un, ue;
+#pragma unroll
+            for (int v = 0; v < VPL; ++v) un.q[v] = add4(add4(Xout.q[v], e.q[v]), Dout.q[v]);
+            bool exact = lane_needs_exact<LPP, VPL, FULL>(un, ln, mok_n);
+            // U_E is built from the (fast) N'; if that one is kept, so is the sum
+#pragma unroll
+            for (int v = 0; v < VPL; ++v) ue.q[v] = add4(add4(Xin.q[v], tn.q[v]), Din.q[v]);
+            exact = exact || lane_needs_exact<LPP, VPL, FULL>(ue, ln, mok_e);
+            if (__any_sync(0xffffffffu, exact)) {
+                HSM_DBG(4);
+                normalise<LPP, VPL, FULL>(un, ln);
+                tn = un;
+#pragma unroll
+                for (int v = 0; v < VPL; ++v) ue.q[v] = add4(add4(Xin.q[v], tn.q[v]), Din.q[v]);
+                normalise<LPP, VPL, FULL>(ue, ln);
+                t = ue;
+            }
+        }
+        const bool upper = (y > yb0);          // row y-1 belongs to this band
+        if (upper) {
+            if (st_n) stage_out(st_np, par, tn);
+            if (st_e) stage_out(st_ep, par, t);
+        }
+        row_off += row_stride;
+    };
+
+    for (int y = yb0;; y += 2) {
+        step(y, 0, S0, S1, X0, X1, D0, D1);
+        if (y == yb1 + 1) break;
+        step(y + 1, 1, S1, S0, X1, X0, D1, D0);
+        if (y == yb1) break;
+    }
+    // the last step staged N'(yb1), E'(yb1) in buffer parity of row yb1+1
+    tma_store_fence();
+    if (tid == 0) tma_store_wait_read();
+    __syncthreads();
+    if (tid == 0) {
+        const int last_par = (yb1 + 1 - yb0) & 1;
+        tma_store_row(&tsN, 1, last_par, yb1);
+        tma_store_row(&tsE, 2, last_par, yb1);
+        tma_store_commit();
+        tma_store_wait_read();
+    }
+}
+
+}  // namespace hsm

@@ -57,7 +57,9 @@ extern "C" {
                                  2 = fused iteration fed by TMA (falls back to 1 if n_levels > 256),
                                  3 = two iterations per launch through a shared-memory row ring
                                      (falls back to 2 for an odd leftover / unsupported shapes),
-                                 4 = like 2 with a TMA producer warp and warp-to-warp exchange (no CTA barrier) */
+                                 4 = like 2 with a TMA producer warp and warp-to-warp exchange (no CTA barrier),
+                                 5 = like 2 with TMA stores (results staged in shared memory; DEFAULT; falls
+                                     back to 2 when the staging does not fit in shared memory, e.g. n_levels 256) */
 #define HSM_OPT_BAND_ROWS 1   /* rows per CTA band in the fused kernel; 0 = heuristic                */
 #define HSM_OPT_DATA_TERM 2   /* 0 = read the data plane (T28), 1 = recompute it in-kernel (T24, default) */
 #define HSM_OPT_VALID_LO 3    /* row-band mode: first/last local row that is inside the image ...    */

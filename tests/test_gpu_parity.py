@@ -15,8 +15,9 @@ ALL = [(c, True) for c in C.SMALL_CASES] + [(c, False) for c in C.BIG_CASES]
 IDS = [c["name"] for c, _ in ALL]
 # (algorithm, data_term): TMA-fed fused kernel with recomputed data term (default) / with the data plane,
 # LDG-fed fused kernel (both), one kernel per direction
-VARIANTS = [(4, 1), (4, 0), (3, 1), (2, 1), (2, 0), (1, 1), (1, 0), (0, 0)]
-VARIANT_IDS = ["ws_T24", "ws_T28", "tma2_T12", "tma_T24", "tma_T28", "ldg_T24", "ldg_T28", "directional_T80"]
+VARIANTS = [(5, 1), (5, 0), (4, 1), (4, 0), (3, 1), (2, 1), (2, 0), (1, 1), (1, 0), (0, 0)]
+VARIANT_IDS = ["tmast_T24", "tmast_T28", "ws_T24", "ws_T28", "tma2_T12", "tma_T24", "tma_T28", "ldg_T24", "ldg_T28",
+               "directional_T80"]
 
 
 def _factory(hsm, algorithm, data_term, band_rows=0, capacity=1):
@@ -53,7 +54,7 @@ def test_cuda_matches_reference_fixture(hsm, case, small, variant):
 @pytest.mark.parametrize("band_rows", [1, 2, 5, 7])
 def test_band_height_does_not_change_results(hsm, band_rows):
     for case in (C.SMALL_CASES[3], C.SMALL_CASES[12], C.SMALL_CASES[24]):
-        labels, planes = C.run_case(_factory(hsm, {1: 3, 2: 1, 5: 4, 7: 2}[band_rows], 1, band_rows=band_rows), case)
+        labels, planes = C.run_case(_factory(hsm, {1: 3, 2: 5, 5: 4, 7: 2}[band_rows], 1, band_rows=band_rows), case)
         data, _ = C.load_fixture(case)
         assert np.array_equal(labels, data["labels"])
         for name, plane in planes.items():

@@ -38,7 +38,7 @@ want = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__
         "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "launch__waves_per_multiprocessor",
         "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem", "smsp__inst_executed.sum",
         "lts__t_sector_hit_rate.pct", "gpc__cycles_elapsed.avg.per_second", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"]
-summary = ["# ncu --set full --clock-control none -k regex:k_iter_tma -s 60 -c 2 (same bench command)"]
+summary = ["# ncu --set full --clock-control none -k regex:k_iter_tma -s 60 -c 2 (same bench command; matches k_iter_tmast)"]
 vals = {}
 for wname in want:
     for i, hh in enumerate(hdr):
