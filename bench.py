@@ -87,6 +87,14 @@ class ClockSampler(object):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
+    def wait_ready(self, timeout=8.0):
+        """Block until nvidia-smi delivered its first sample (it can take a second to start on an
+        8-GPU box), then remember where the timed region's samples begin."""
+        deadline = time.time() + timeout
+        while self.proc is not None and not self.lines and time.time() < deadline:
+            time.sleep(0.05)
+        self.first = len(self.lines)
+
     def __exit__(self, *exc):
         if self.proc is not None:
             self.proc.terminate()
@@ -97,7 +105,9 @@ class ClockSampler(object):
 
     def summary(self):
         sm, sm_max, power, reasons = [], [], [], set()
-        for line in self.lines:
+        first = getattr(self, "first", 0)
+        lines = self.lines[first:] if len(self.lines) > first else self.lines[-1:]
+        for line in lines:
             parts = [p.strip() for p in line.split(",")]
             if len(parts) < 7:
                 continue
@@ -235,6 +245,8 @@ def main():
     matcher.reset_stats()
     begin, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as clocks:
+        if rank == 0:
+            clocks.wait_ready()
         barrier()
         begin.record(stream)
         for _ in range(args.steps):
