@@ -187,17 +187,17 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1)
             for (int v = 0; v < VPL; ++v) ringd_at(slot_y, v) = DAout.q[v];
             if (y > g.vhi) zero_vec(SAin);
 #pragma unroll
-            for (int v = 0; v < VPL; ++v) t.q[v] = sum4(SAin.q[v], n.q[v], e.q[v], DAout.q[v]);
-            normalise<LPP, VPL, FULL>(t, ln);
+            for (int v = 0; v < VPL; ++v) {
+                t.q[v] = sum4(SAin.q[v], n.q[v], e.q[v], DAout.q[v]);
+                SAnext.q[v] = sum4(w.q[v], n.q[v], e.q[v], DAout.q[v]);
+            }
+            normalise_pair<LPP, VPL, FULL>(t, SAnext, ln);
             if (mask_w) zero_vec(t);
             if (px >= 1) {
 #pragma unroll
                 for (int v = 0; v < VPL; ++v)
                     if (FULL || ln.active[v]) ring_at(0, slot_y, px - 1, v) = t.q[v];
             }
-#pragma unroll
-            for (int v = 0; v < VPL; ++v) SAnext.q[v] = sum4(w.q[v], n.q[v], e.q[v], DAout.q[v]);
-            normalise<LPP, VPL, FULL>(SAnext, ln);
         }
         // ---------------- stage B, part 1: row r from the ring, publish W''(r, x-1), S''(r+1) -----
         Vec<VPL> wb, nb, eb;
@@ -214,18 +214,19 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1)
                 DBout.q[v] = ringd_at(slot_r, v);
             }
             if (r > g.vhi) zero_vec(SBin);
+#pragma unroll
+            for (int v = 0; v < VPL; ++v) SBnext.q[v] = sum4(wb.q[v], nb.q[v], eb.q[v], DBout.q[v]);
             if (r >= yb0) {
 #pragma unroll
                 for (int v = 0; v < VPL; ++v) t.q[v] = sum4(SBin.q[v], nb.q[v], eb.q[v], DBout.q[v]);
-                normalise<LPP, VPL, FULL>(t, ln);
+                normalise_pair<LPP, VPL, FULL>(t, SBnext, ln);
                 if (mask_w) zero_vec(t);
 #pragma unroll
                 for (int v = 0; v < VPL; ++v) ex(par, v, tid) = t.q[v];
                 if (st_w && r <= yb1) store_at(Wout, row_off - (unsigned)g.Dp, t);
+            } else {
+                normalise_checked<LPP, VPL, FULL>(SBnext, ln);
             }
-#pragma unroll
-            for (int v = 0; v < VPL; ++v) SBnext.q[v] = sum4(wb.q[v], nb.q[v], eb.q[v], DBout.q[v]);
-            normalise<LPP, VPL, FULL>(SBnext, ln);
             if (STORE_S && st_n && r + 1 >= yb0 && r + 1 <= yb1) store_at(Sout, row_off + row_stride, SBnext);
         }
         // ---------------- one barrier for both exchanges -----------------------------------------
@@ -241,16 +242,20 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1)
 #pragma unroll
             for (int v = 0; v < VPL; ++v)
                 XAout.q[v] = (FULL || ln.active[v]) ? add4(SAin.q[v], ring_at(0, slot_y, px, v)) : zero4();
+            Vec<VPL> tn;
 #pragma unroll
-            for (int v = 0; v < VPL; ++v) t.q[v] = add4(add4(XAout.q[v], e.q[v]), DAout.q[v]);
-            normalise<LPP, VPL, FULL>(t, ln);
-            if (y - 1 < g.vlo) zero_vec(t);                 // block-uniform: the row above the image receives nothing
+            for (int v = 0; v < VPL; ++v) tn.q[v] = add4(add4(XAout.q[v], e.q[v]), DAout.q[v]);
+            if (y - 1 < g.vlo) {                            // block-uniform: the row above the image receives nothing
+                zero_vec(tn);
+#pragma unroll
+                for (int v = 0; v < VPL; ++v) t.q[v] = add4(add4(XAin.q[v], tn.q[v]), DAin.q[v]);
+                normalise<LPP, VPL, FULL>(t, ln);
+            } else {
+                normalise_chain<LPP, VPL, FULL>(tn, t, XAin, DAin, ln);
+            }
 #pragma unroll
             for (int v = 0; v < VPL; ++v)
-                if (FULL || ln.active[v]) ring_at(1, slot_ym1, px, v) = t.q[v];
-#pragma unroll
-            for (int v = 0; v < VPL; ++v) t.q[v] = add4(add4(XAin.q[v], t.q[v]), DAin.q[v]);
-            normalise<LPP, VPL, FULL>(t, ln);
+                if (FULL || ln.active[v]) ring_at(1, slot_ym1, px, v) = tn.q[v];
             if (mask_e) zero_vec(t);
             if (px + 1 < PX) {
 #pragma unroll
@@ -263,14 +268,12 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1)
             const int rd = (px + 1 < PX) ? tid + LPP : NT + ln.c;      // last pixel group reads the zero slot
 #pragma unroll
             for (int v = 0; v < VPL; ++v) XBout.q[v] = add4(SBin.q[v], ex(par, v, rd));
+            Vec<VPL> tnb;
 #pragma unroll
-            for (int v = 0; v < VPL; ++v) t.q[v] = add4(add4(XBout.q[v], eb.q[v]), DBout.q[v]);
-            normalise<LPP, VPL, FULL>(t, ln);
+            for (int v = 0; v < VPL; ++v) tnb.q[v] = add4(add4(XBout.q[v], eb.q[v]), DBout.q[v]);
+            normalise_chain<LPP, VPL, FULL>(tnb, t, XBin, DBin, ln);
             const bool upper = (r > yb0);
-            if (upper && st_n) store_at(Nout, row_off - row_stride, t);
-#pragma unroll
-            for (int v = 0; v < VPL; ++v) t.q[v] = add4(add4(XBin.q[v], t.q[v]), DBin.q[v]);
-            normalise<LPP, VPL, FULL>(t, ln);
+            if (upper && st_n) store_at(Nout, row_off - row_stride, tnb);
             if (upper && st_e) store_at(Eout, row_off - row_stride + (unsigned)g.Dp, t);
         }
         row_off += row_stride;
