@@ -301,12 +301,15 @@ int choose_band_rows(const hsm_matcher *m, int strips)
 {
     const int rows = m->ohi - m->olo + 1;
     if (m->band_rows > 0) return std::min(m->band_rows, rows);
-    // aim for ~16 CTAs per SM over the whole launch (several waves, short tail), bands of at
-    // least 12 rows (each band re-reads 2 halo rows)
-    const long target = 148L * 16;
+    // Aim for ~16 CTAs per SM over the whole launch (several waves, short tail).  Every band re-reads
+    // two halo rows, so bands are normally at least 12 rows; when even 12-row bands cannot fill the
+    // machine once (a single small frame: latency-, not bandwidth-bound) they may shrink to 4 rows.
     const long per_band = (long)strips * m->frames;
+    int min_rows = 12;
+    while (min_rows > 4 && per_band * ((rows + min_rows - 1) / min_rows) < 148L * 3) min_rows -= 2;
+    const long target = 148L * 16;
     long bands = (target + per_band - 1) / per_band;
-    bands = std::max(1L, std::min<long>(bands, std::max(1, rows / 12)));
+    bands = std::max(1L, std::min<long>(bands, std::max(1, rows / min_rows)));
     return (int)((rows + bands - 1) / bands);
 }
 
