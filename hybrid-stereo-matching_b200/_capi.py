@@ -33,7 +33,7 @@ class Stats(ctypes.Structure):
 
 
 def _sources():
-    return [os.path.join(_CSRC, f) for f in sorted(os.listdir(_CSRC)) if f.endswith((".cu", ".cuh"))] \
+    return [os.path.join(_CSRC, f) for f in sorted(os.listdir(_CSRC)) if f.endswith((".cu", ".cuh", ".hpp"))] \
         + [HEADER_PATH]
 
 
@@ -44,20 +44,37 @@ def library_is_stale():
     return any(os.path.getmtime(src) > built for src in _sources())
 
 
-def build_library(force=False, verbose=False):
-    """Compile csrc/*.cu into libhsm_b200.so for sm_100a (works without a GPU)."""
+def build_library(force=False, verbose=False, jobs=None):
+    """Compile csrc/*.cu into libhsm_b200.so for sm_100a (works without a GPU).  The translation
+    units (C ABI + one per iteration-kernel family) are compiled in parallel, then linked."""
     if not force and not library_is_stale():
         return LIB_PATH
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found: cannot build %s" % LIB_PATH)
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-          ["-o", LIB_PATH, os.path.join(_CSRC, "hsm_api.cu")]
-    proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, universal_newlines=True)
+    units = [f for f in sorted(os.listdir(_CSRC)) if f.endswith(".cu")]
+    obj_dir = os.path.join(_PKG_DIR, "build")
+    os.makedirs(obj_dir, exist_ok=True)
+    compile_flags = [flag for flag in NVCC_FLAGS if flag != "-shared"] + (["-Xptxas", "-v"] if verbose else [])
+
+    def compile_unit(unit):
+        obj = os.path.join(obj_dir, unit[:-3] + ".o")
+        cmd = [nvcc] + compile_flags + ["-c", "-o", obj, os.path.join(_CSRC, unit)]
+        proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, universal_newlines=True)
+        return unit, obj, proc.returncode, proc.stdout
+
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=jobs or min(len(units), os.cpu_count() or 1)) as pool:
+        results = list(pool.map(compile_unit, units))
+    for unit, _, code, output in results:
+        if code != 0:
+            raise RuntimeError("nvcc failed on %s:\n%s" % (unit, output))
+        if verbose:
+            print(output)
+    link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_PATH] + [r[1] for r in results]
+    proc = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, universal_newlines=True)
     if proc.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + proc.stdout)
-    if verbose:
-        print(proc.stdout)
+        raise RuntimeError("link failed:\n" + proc.stdout)
     return LIB_PATH
 
 

@@ -6,29 +6,17 @@
 // of neighbouring pixels, so it cannot update in place); the float32 images and
 // the int32 prior labels; staging space for callers' float64 / int64 arrays.
 // Everything is allocated lazily on the first compute call (fork safety).
-#include "../../include/hsm.h"
-
-#include <cuda_runtime.h>
-
-#include <algorithm>
-#include <cstdarg>
-#include <cstdio>
-#include <cstring>
-#include <string>
-#include <vector>
-
-#include "kernels.cuh"
-#include "iter_tma.cuh"
-#include "iter2_tma.cuh"
-#include "iter_ws.cuh"
-#include "iter_tma_st.cuh"
+// The iteration kernels are launched from their own translation units (matcher.hpp).
+#include "matcher.hpp"
 #include "raster.cuh"
 
 using namespace hsm;
 
 namespace {
-
 thread_local std::string g_error;
+}
+
+namespace hsm {
 
 int fail(int code, const char *fmt, ...)
 {
@@ -41,19 +29,9 @@ int fail(int code, const char *fmt, ...)
     return code;
 }
 
-#define CUDA_TRY(expr)                                                                            \
-    do {                                                                                          \
-        cudaError_t err__ = (expr);                                                               \
-        if (err__ != cudaSuccess)                                                                 \
-            return fail(HSM_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(err__),  \
-                        __FILE__, __LINE__);                                                      \
-    } while (0)
+}  // namespace hsm
 
-#define HSM_TRY(expr)                    \
-    do {                                 \
-        int rc__ = (expr);               \
-        if (rc__ != HSM_OK) return rc__; \
-    } while (0)
+namespace {
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -68,10 +46,6 @@ size_t dtype_size(int dtype)
 
 // Lane configuration for a disparity range: LPP lanes per pixel, VPL float4 per lane,
 // NT threads per CTA of the fused kernel.
-struct LaneCfg {
-    int lpp, vpl, nt;
-};
-
 // Table of lane configurations (index = HSM_OPT_LANE_CONFIG - 1).  Entries 0..5 are the
 // defaults per disparity range; 6..8 trade lanes per pixel for float4s per lane (fewer
 // shuffle steps and per-pixel operations per element, more registers per thread).
@@ -94,58 +68,6 @@ bool lane_cfg(int D, LaneCfg *c)
     *c = kLaneTable[pick];
     return true;
 }
-
-// Run `body` with LPP, VPL, NT as compile-time constants.
-#define HSM_DISPATCH_CASE(l, v, n, ...) \
-    if ((cfg__).lpp == l && (cfg__).vpl == v) { constexpr int LPP = l, VPL = v, NT = n; __VA_ARGS__ }
-#define HSM_DISPATCH(cfg, ...)                                  \
-    do {                                                        \
-        const LaneCfg cfg__ = (cfg);                            \
-        HSM_DISPATCH_CASE(4, 1, 256, __VA_ARGS__)               \
-        else HSM_DISPATCH_CASE(8, 1, 256, __VA_ARGS__)          \
-        else HSM_DISPATCH_CASE(16, 1, 512, __VA_ARGS__)         \
-        else HSM_DISPATCH_CASE(32, 1, 512, __VA_ARGS__)         \
-        else HSM_DISPATCH_CASE(32, 2, 512, __VA_ARGS__)         \
-        else HSM_DISPATCH_CASE(32, 4, 256, __VA_ARGS__)         \
-        else HSM_DISPATCH_CASE(4, 2, 256, __VA_ARGS__)          \
-        else HSM_DISPATCH_CASE(8, 2, 256, __VA_ARGS__)          \
-        else HSM_DISPATCH_CASE(16, 2, 512, __VA_ARGS__)         \
-    } while (0)
-
-}  // namespace
-
-struct hsm_matcher {
-    int H = 0, W = 0, Wp = 0, D = 0, Dp = 0, cap = 0, device = 0;
-    LaneCfg cfg{};
-    bool ready = false;
-    cudaStream_t stream = nullptr;
-    bool own_stream = false;
-    void *arena = nullptr;
-    size_t arena_bytes = 0;
-    float *S = nullptr, *Wm[2] = {nullptr, nullptr}, *Nm[2] = {nullptr, nullptr}, *Em[2] = {nullptr, nullptr};
-    float *Dt = nullptr;
-    float *L = nullptr, *R = nullptr;
-    int *P = nullptr;
-    char *stage[3] = {nullptr, nullptr, nullptr};
-    long long *labels = nullptr;
-    int cur = 0;          // which of the double buffers holds the current W, N, E
-    int frames = 0;       // frames of the current batch
-    bool have_fields = false, have_prior = false, dt_valid = false, s_valid = true;
-    Blend blend{kPriorNone, 0.0f, 0.0};
-    // options
-    int algorithm = 5, band_rows = 0, data_term = 1, stages = 0, lane_config = 0;
-    // TMA descriptors of the double-buffered planes (algorithm 2)
-    CUtensorMap tmW[2], tmN[2], tmE[2], tmD;
-    CUtensorMap tsW[2], tsN[2], tsE[2];          // store maps (box = TX output pixels)
-    ImageMaps tmI;
-    bool maps_valid = false;
-    int vlo = 0, vhi = 0, olo = 0, ohi = 0;
-    // statistics
-    hsm_stats stats{};
-    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending, pool;
-};
-
-namespace {
 
 size_t plane_floats(const hsm_matcher *m) { return (size_t)m->cap * m->H * m->W * m->Dp; }
 size_t image_elems(const hsm_matcher *m) { return (size_t)m->cap * m->H * m->Wp; }
@@ -194,6 +116,9 @@ int ensure_ready(hsm_matcher *m)
     return HSM_OK;
 }
 
+}  // namespace
+
+namespace hsm {
 Geo geometry(const hsm_matcher *m)
 {
     Geo g;
@@ -203,6 +128,9 @@ Geo geometry(const hsm_matcher *m)
     g.image_stride = (size_t)m->H * m->Wp;
     return g;
 }
+}  // namespace hsm
+
+namespace {
 
 int pixel_grid(const hsm_matcher *m, int lpp)
 {
@@ -212,6 +140,9 @@ int pixel_grid(const hsm_matcher *m, int lpp)
     return (int)std::min<size_t>(blocks, (size_t)148 * 64);
 }
 
+}  // namespace
+
+namespace hsm {
 int check_launch(hsm_matcher *m, const char *what)
 {
     cudaError_t err = cudaGetLastError();
@@ -219,6 +150,9 @@ int check_launch(hsm_matcher *m, const char *what)
     m->stats.kernel_launches++;
     return HSM_OK;
 }
+}  // namespace hsm
+
+namespace {
 
 int ensure_data_plane(hsm_matcher *m)
 {
@@ -297,6 +231,9 @@ int load_prior(hsm_matcher *m, const void *src, int dtype, size_t n, int on_devi
     return check_launch(m, "k_prior_labels");
 }
 
+}  // namespace
+
+namespace hsm {
 int choose_band_rows(const hsm_matcher *m, int strips)
 {
     const int rows = m->ohi - m->olo + 1;
@@ -312,39 +249,9 @@ int choose_band_rows(const hsm_matcher *m, int strips)
     bands = std::max(1L, std::min<long>(bands, std::max(1, rows / min_rows)));
     return (int)((rows + bands - 1) / bands);
 }
+}  // namespace hsm
 
-template <int LPP, int VPL, int NT>
-int launch_fused(hsm_matcher *m, bool store_s)
-{
-    const Geo g = geometry(m);
-    constexpr int TX = NT / LPP - 2;
-    const int strips = (m->W + TX - 1) / TX;
-    IterArgs a;
-    a.Win = m->Wm[m->cur]; a.Nin = m->Nm[m->cur]; a.Ein = m->Em[m->cur];
-    a.Wout = m->Wm[m->cur ^ 1]; a.Nout = m->Nm[m->cur ^ 1]; a.Eout = m->Em[m->cur ^ 1];
-    a.Sout = m->S;
-    a.Dt = m->Dt; a.L = m->L; a.R = m->R; a.P = m->have_prior ? m->P : nullptr;
-    a.blend = m->blend;
-    a.olo = m->olo; a.ohi = m->ohi;
-    a.band_rows = choose_band_rows(m, strips);
-    const int bands = (m->ohi - m->olo + 1 + a.band_rows - 1) / a.band_rows;
-    dim3 grid(strips, bands, m->frames);
-    const bool dt_load = (m->data_term == 0);
-    const bool full = (m->D == 4 * LPP * VPL);
-    a.store_s = store_s ? 1 : 0;
-    a.has_prior = m->have_prior ? 1 : 0;
-    if (full) {
-        if (dt_load) k_iter_fused<LPP, VPL, NT, true, true><<<grid, NT, 0, m->stream>>>(g, a);
-        else k_iter_fused<LPP, VPL, NT, false, true><<<grid, NT, 0, m->stream>>>(g, a);
-    } else {
-        if (dt_load) k_iter_fused<LPP, VPL, NT, true, false><<<grid, NT, 0, m->stream>>>(g, a);
-        else k_iter_fused<LPP, VPL, NT, false, false><<<grid, NT, 0, m->stream>>>(g, a);
-    }
-    HSM_TRY(check_launch(m, "k_iter_fused"));
-    m->stats.iteration_launches++;
-    m->cur ^= 1;
-    return HSM_OK;
-}
+namespace {
 
 #ifndef HSM_L2_PROMOTION
 #define HSM_L2_PROMOTION CU_TENSOR_MAP_L2_PROMOTION_L2_128B
@@ -405,8 +312,32 @@ int make_image_map(const hsm_matcher *m, CUtensorMap *map, void *image, bool is_
     return HSM_OK;
 }
 
+}  // namespace
+
+namespace hsm {
 bool tma_supported(const hsm_matcher *m) { return m->Dp <= 256 && m->cfg.lpp * m->cfg.vpl * 4 <= 256; }
 
+IterArgs iter_args(hsm_matcher *m, int strips, bool store_s)
+{
+    IterArgs a;
+    a.Win = m->Wm[m->cur]; a.Nin = m->Nm[m->cur]; a.Ein = m->Em[m->cur];
+    a.Wout = m->Wm[m->cur ^ 1]; a.Nout = m->Nm[m->cur ^ 1]; a.Eout = m->Em[m->cur ^ 1];
+    a.Sout = m->S;
+    a.Dt = m->Dt; a.L = m->L; a.R = m->R; a.P = m->have_prior ? m->P : nullptr;
+    a.blend = m->blend;
+    a.olo = m->olo; a.ohi = m->ohi;
+    a.band_rows = choose_band_rows(m, strips);
+    a.store_s = store_s ? 1 : 0;
+    a.has_prior = m->have_prior ? 1 : 0;
+    return a;
+}
+}  // namespace hsm
+
+namespace {
+
+}  // namespace
+
+namespace hsm {
 int ensure_maps(hsm_matcher *m)
 {
     if (m->maps_valid) return HSM_OK;
@@ -431,202 +362,9 @@ int ensure_maps(hsm_matcher *m)
     m->maps_valid = true;
     return HSM_OK;
 }
+}  // namespace hsm
 
-template <int LPP, int VPL, int NT>
-int launch_tma(hsm_matcher *m, bool store_s)
-{
-    HSM_TRY(ensure_maps(m));
-    const Geo g = geometry(m);
-    constexpr int PX = NT / LPP, TX = PX - 2, SLOTS = NT + 2 * LPP;
-    const int strips = (m->W + TX - 1) / TX;
-    IterArgs a;
-    a.Win = m->Wm[m->cur]; a.Nin = m->Nm[m->cur]; a.Ein = m->Em[m->cur];
-    a.Wout = m->Wm[m->cur ^ 1]; a.Nout = m->Nm[m->cur ^ 1]; a.Eout = m->Em[m->cur ^ 1];
-    a.Sout = m->S;
-    a.Dt = m->Dt; a.L = m->L; a.R = m->R; a.P = m->have_prior ? m->P : nullptr;
-    a.blend = m->blend;
-    a.olo = m->olo; a.ohi = m->ohi;
-    a.band_rows = choose_band_rows(m, strips);
-    const int bands = (m->ohi - m->olo + 1 + a.band_rows - 1) / a.band_rows;
-    dim3 grid(strips, bands, m->frames);
-    const bool dt_load = (m->data_term == 0);
-    const bool full = (m->D == 4 * LPP * VPL);
-    a.store_s = store_s ? 1 : 0;
-    a.has_prior = m->have_prior ? 1 : 0;
-    (void)PX;
-    const size_t stage_bytes = StageLayout<LPP, VPL, NT>::stage_bytes(m->Dp, dt_load);
-    const size_t fixed_bytes = (size_t)2 * VPL * SLOTS * 16 + 128;   // exchange slots + mbarriers
-    int stages = m->stages;
-    if (stages <= 0) {      // as many stages (2..3) as fit the per-CTA share of shared memory
-        const int target_ctas = (NT == 256) ? (VPL == 1 ? 4 : 2) : (VPL == 1 ? 2 : 1);
-        const size_t budget = (size_t)227 * 1024 / target_ctas - 1024;
-        stages = 3;
-        while (stages > 2 && fixed_bytes + stages * stage_bytes > budget) --stages;
-    }
-    const size_t smem = fixed_bytes + (size_t)stages * stage_bytes;
-    if (smem > (size_t)227 * 1024) return fail(HSM_ERR_ARG, "fused TMA kernel needs %zu bytes of shared memory", smem);
-    const CUtensorMap &tw = m->tmW[m->cur], &tn = m->tmN[m->cur], &te = m->tmE[m->cur], &td = m->tmD;
-#define HSM_LAUNCH_TMA(T, F)                                                                                 \
-    do {                                                                                                     \
-        auto kernel = k_iter_tma<LPP, VPL, NT, T, F>;                                                        \
-        CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
-        kernel<<<grid, NT, smem, m->stream>>>(tw, tn, te, td, m->tmI.L, m->tmI.R, m->tmI.P, g, a, stages);                         \
-    } while (0)
-    if (full) { if (dt_load) HSM_LAUNCH_TMA(true, true); else HSM_LAUNCH_TMA(false, true); }
-    else { if (dt_load) HSM_LAUNCH_TMA(true, false); else HSM_LAUNCH_TMA(false, false); }
-#undef HSM_LAUNCH_TMA
-    HSM_TRY(check_launch(m, "k_iter_tma"));
-    m->stats.iteration_launches++;
-    m->cur ^= 1;
-    return HSM_OK;
-}
-
-// Two iterations per launch (algorithm 3).  Returns HSM_OK and sets *launched = false when the
-// configuration cannot use it (caller falls back to one iteration per launch).
-template <int LPP, int VPL, int NT>
-int launch_tma2(hsm_matcher *m, bool store_s, bool *launched)
-{
-    *launched = false;
-    constexpr int PX = NT / LPP, TX = PX - 4, SLOTS = NT + LPP;
-    if (TX < 4) return HSM_OK;
-    const size_t stage_bytes = StageLayout<LPP, VPL, NT>::stage_bytes(m->Dp, false);
-    const size_t fixed_bytes = Ring2Layout<LPP, VPL, NT>::ring_bytes(m->Dp) + (size_t)2 * VPL * SLOTS * 16 + 128;
-    int stages = m->stages > 0 ? m->stages : 3;
-    while (stages > 2 && fixed_bytes + stages * stage_bytes > (size_t)113 * 1024) --stages;
-    const size_t smem = fixed_bytes + (size_t)stages * stage_bytes;
-    if (smem > (size_t)227 * 1024) return HSM_OK;
-    HSM_TRY(ensure_maps(m));
-    const Geo g = geometry(m);
-    const int strips = (m->W + TX - 1) / TX;
-    IterArgs a;
-    a.Win = m->Wm[m->cur]; a.Nin = m->Nm[m->cur]; a.Ein = m->Em[m->cur];
-    a.Wout = m->Wm[m->cur ^ 1]; a.Nout = m->Nm[m->cur ^ 1]; a.Eout = m->Em[m->cur ^ 1];
-    a.Sout = m->S;
-    a.Dt = m->Dt; a.L = m->L; a.R = m->R; a.P = m->have_prior ? m->P : nullptr;
-    a.blend = m->blend;
-    a.olo = m->olo; a.ohi = m->ohi;
-    a.band_rows = choose_band_rows(m, strips);
-    a.store_s = store_s ? 1 : 0;
-    a.has_prior = m->have_prior ? 1 : 0;
-    const int bands = (m->ohi - m->olo + 1 + a.band_rows - 1) / a.band_rows;
-    dim3 grid(strips, bands, m->frames);
-    const bool full = (m->D == 4 * LPP * VPL);
-    const CUtensorMap &tw = m->tmW[m->cur], &tn = m->tmN[m->cur], &te = m->tmE[m->cur];
-#define HSM_LAUNCH_TMA2(F)                                                                                   \
-    do {                                                                                                     \
-        auto kernel = k_iter2_tma<LPP, VPL, NT, F>;                                                          \
-        CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
-        kernel<<<grid, NT, smem, m->stream>>>(tw, tn, te, m->tmI.L, m->tmI.R, m->tmI.P, g, a, stages);       \
-    } while (0)
-    if (full) HSM_LAUNCH_TMA2(true); else HSM_LAUNCH_TMA2(false);
-#undef HSM_LAUNCH_TMA2
-    HSM_TRY(check_launch(m, "k_iter2_tma"));
-    m->stats.iteration_launches++;
-    m->cur ^= 1;
-    *launched = true;
-    return HSM_OK;
-}
-
-// Warp-specialised variant (algorithm 4): NT consumer threads + one producer warp.
-template <int LPP, int VPL, int NT>
-int launch_ws(hsm_matcher *m, bool store_s)
-{
-    HSM_TRY(ensure_maps(m));
-    const Geo g = geometry(m);
-    constexpr int PX = NT / LPP, TX = PX - 2, NW = NT / 32, XR = 4;
-    const int strips = (m->W + TX - 1) / TX;
-    IterArgs a;
-    a.Win = m->Wm[m->cur]; a.Nin = m->Nm[m->cur]; a.Ein = m->Em[m->cur];
-    a.Wout = m->Wm[m->cur ^ 1]; a.Nout = m->Nm[m->cur ^ 1]; a.Eout = m->Em[m->cur ^ 1];
-    a.Sout = m->S;
-    a.Dt = m->Dt; a.L = m->L; a.R = m->R; a.P = m->have_prior ? m->P : nullptr;
-    a.blend = m->blend;
-    a.olo = m->olo; a.ohi = m->ohi;
-    a.band_rows = choose_band_rows(m, strips);
-    a.store_s = store_s ? 1 : 0;
-    a.has_prior = m->have_prior ? 1 : 0;
-    const int bands = (m->ohi - m->olo + 1 + a.band_rows - 1) / a.band_rows;
-    dim3 grid(strips, bands, m->frames);
-    const bool dt_load = (m->data_term == 0);
-    const bool full = (m->D == 4 * LPP * VPL);
-    const size_t stage_bytes = StageLayout<LPP, VPL, NT>::stage_bytes(m->Dp, dt_load);
-    const size_t fixed_bytes = (size_t)NW * XR * VPL * LPP * 16 + (size_t)(2 * 3 + NW * XR) * 8 + 128;
-    int stages = m->stages > 0 ? std::min(m->stages, 3) : 3;      // the exchange ring holds stages + 1 rows
-    {
-        const int target_ctas = (NT == 256) ? (VPL == 1 ? 4 : 2) : (VPL == 1 ? 2 : 1);
-        const size_t budget = (size_t)227 * 1024 / target_ctas - 1024;
-        while (stages > 2 && fixed_bytes + stages * stage_bytes > budget) --stages;
-    }
-    const size_t smem = fixed_bytes + (size_t)stages * stage_bytes;
-    if (smem > (size_t)227 * 1024) return fail(HSM_ERR_ARG, "warp-specialised kernel needs %zu bytes of shared memory", smem);
-    const CUtensorMap &tw = m->tmW[m->cur], &tn = m->tmN[m->cur], &te = m->tmE[m->cur], &td = m->tmD;
-#define HSM_LAUNCH_WS(T, F)                                                                                  \
-    do {                                                                                                     \
-        auto kernel = k_iter_ws<LPP, VPL, NT, T, F>;                                                         \
-        CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
-        kernel<<<grid, NT + 32, smem, m->stream>>>(tw, tn, te, td, m->tmI.L, m->tmI.R, m->tmI.P, g, a, stages); \
-    } while (0)
-    if (full) { if (dt_load) HSM_LAUNCH_WS(true, true); else HSM_LAUNCH_WS(false, true); }
-    else { if (dt_load) HSM_LAUNCH_WS(true, false); else HSM_LAUNCH_WS(false, false); }
-#undef HSM_LAUNCH_WS
-    HSM_TRY(check_launch(m, "k_iter_ws"));
-    m->stats.iteration_launches++;
-    m->cur ^= 1;
-    return HSM_OK;
-}
-
-// TMA-load + TMA-store variant (algorithm 5).  *launched = false if its shared memory does not fit.
-template <int LPP, int VPL, int NT>
-int launch_tmast(hsm_matcher *m, bool store_s, bool *launched)
-{
-    *launched = false;
-    constexpr int PX = NT / LPP, TX = PX - 2, SLOTS = NT + 2 * LPP;
-    const bool dt_load = (m->data_term == 0);
-    const size_t stage_bytes = StageLayout<LPP, VPL, NT>::stage_bytes(m->Dp, dt_load);
-    const size_t ost_bytes = ((size_t)TX * m->Dp * 4 + 127) & ~(size_t)127;
-    const size_t fixed_bytes = 6 * ost_bytes + (size_t)2 * VPL * SLOTS * 16 + 128;
-    int stages = m->stages;
-    if (stages <= 0) {
-        const int target_ctas = (NT == 256) ? (VPL == 1 ? 3 : 2) : (VPL == 1 ? 2 : 1);
-        const size_t budget = (size_t)227 * 1024 / target_ctas - 1024;
-        stages = 3;
-        while (stages > 2 && fixed_bytes + stages * stage_bytes > budget) --stages;
-    }
-    const size_t smem = fixed_bytes + (size_t)stages * stage_bytes;
-    if (smem > (size_t)227 * 1024) return HSM_OK;
-    HSM_TRY(ensure_maps(m));
-    const Geo g = geometry(m);
-    const int strips = (m->W + TX - 1) / TX;
-    IterArgs a;
-    a.Win = m->Wm[m->cur]; a.Nin = m->Nm[m->cur]; a.Ein = m->Em[m->cur];
-    a.Wout = m->Wm[m->cur ^ 1]; a.Nout = m->Nm[m->cur ^ 1]; a.Eout = m->Em[m->cur ^ 1];
-    a.Sout = m->S;
-    a.Dt = m->Dt; a.L = m->L; a.R = m->R; a.P = m->have_prior ? m->P : nullptr;
-    a.blend = m->blend;
-    a.olo = m->olo; a.ohi = m->ohi;
-    a.band_rows = choose_band_rows(m, strips);
-    a.store_s = store_s ? 1 : 0;
-    a.has_prior = m->have_prior ? 1 : 0;
-    const int bands = (m->ohi - m->olo + 1 + a.band_rows - 1) / a.band_rows;
-    dim3 grid(strips, bands, m->frames);
-    const bool full = (m->D == 4 * LPP * VPL);
-    const int in = m->cur, out = m->cur ^ 1;
-#define HSM_LAUNCH_TMAST(T, F)                                                                               \
-    do {                                                                                                     \
-        auto kernel = k_iter_tmast<LPP, VPL, NT, T, F>;                                                      \
-        CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
-        kernel<<<grid, NT, smem, m->stream>>>(m->tmW[in], m->tmN[in], m->tmE[in], m->tmD, m->tmI.L, m->tmI.R, \
-                                              m->tmI.P, m->tsW[out], m->tsN[out], m->tsE[out], g, a, stages);  \
-    } while (0)
-    if (full) { if (dt_load) HSM_LAUNCH_TMAST(true, true); else HSM_LAUNCH_TMAST(false, true); }
-    else { if (dt_load) HSM_LAUNCH_TMAST(true, false); else HSM_LAUNCH_TMAST(false, false); }
-#undef HSM_LAUNCH_TMAST
-    HSM_TRY(check_launch(m, "k_iter_tmast"));
-    m->stats.iteration_launches++;
-    m->cur ^= 1;
-    *launched = true;
-    return HSM_OK;
-}
+namespace {
 
 int launch_directional(hsm_matcher *m)
 {
@@ -668,7 +406,6 @@ float *plane_ptr(hsm_matcher *m, int which)
 }
 
 }  // namespace
-
 extern "C" {
 
 int hsm_version(void) { return 100; }
@@ -862,21 +599,21 @@ int hsm_iterate(hsm_matcher *m, int n_iter, int finalize)
         if (m->algorithm == 3 && tma_supported(m) && m->data_term == 1 && left >= 2 && left % 2 == 0) {
             bool launched = false;
             const bool store_s2 = finalize && left == 2;
-            HSM_DISPATCH(m->cfg, { HSM_TRY((launch_tma2<LPP, VPL, NT>(m, store_s2, &launched))); });
+            HSM_TRY(launch_tma2_any(m, store_s2, &launched));
             if (launched) { ++it; continue; }
         }
         const bool store_s = finalize && (it == n_iter - 1);
         if (m->algorithm == 5 && tma_supported(m)) {
             bool launched = false;
-            HSM_DISPATCH(m->cfg, { HSM_TRY((launch_tmast<LPP, VPL, NT>(m, store_s, &launched))); });
+            HSM_TRY(launch_tmast_any(m, store_s, &launched));
             if (launched) continue;
         }
         if (m->algorithm == 4 && tma_supported(m))
-            HSM_DISPATCH(m->cfg, { HSM_TRY((launch_ws<LPP, VPL, NT>(m, store_s))); });
+            HSM_TRY(launch_ws_any(m, store_s));
         else if (m->algorithm >= 2 && tma_supported(m))
-            HSM_DISPATCH(m->cfg, { HSM_TRY((launch_tma<LPP, VPL, NT>(m, store_s))); });
+            HSM_TRY(launch_tma_any(m, store_s));
         else
-            HSM_DISPATCH(m->cfg, { HSM_TRY((launch_fused<LPP, VPL, NT>(m, store_s))); });
+            HSM_TRY(launch_fused_any(m, store_s));
     }
     CUDA_TRY(cudaEventRecord(ev.second, m->stream));
     m->pending.push_back(ev);
@@ -1134,15 +871,6 @@ int hsm_selftest_division(const float *a4, const float *b, size_t n, unsigned lo
     return HSM_OK;
 }
 
-#ifdef HSM_DEBUG_COUNT
-int hsm_debug_counters(unsigned long long *out8, int reset)
-{
-    CUDA_TRY(cudaDeviceSynchronize());
-    CUDA_TRY(cudaMemcpyFromSymbol(out8, hsm::g_dbg, 8 * sizeof(unsigned long long)));
-    if (reset) { unsigned long long z[8] = {0}; CUDA_TRY(cudaMemcpyToSymbol(hsm::g_dbg, z, sizeof z)); }
-    return HSM_OK;
-}
-#endif
 
 int hsm_host_alloc(size_t bytes, void **out)
 {
@@ -1158,3 +886,4 @@ int hsm_host_free(void *p)
 }
 
 }  // extern "C"
+

@@ -72,12 +72,6 @@ __device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *map, u
         : "memory");
 }
 
-#ifdef HSM_DEBUG_COUNT
-__device__ unsigned long long g_dbg[8];
-#define HSM_DBG(i) do { if ((threadIdx.x & 31) == 0) atomicAdd(&g_dbg[i], 1ull); } while (0)
-#else
-#define HSM_DBG(i) do { } while (0)
-#endif
 #ifndef HSM_TMA_MIN_BLOCKS
 #define HSM_TMA_MIN_BLOCKS 3
 #endif
@@ -102,10 +96,6 @@ struct StageLayout {
     {
         return planes_bytes(Dp, dt_load) + (dt_load ? 0u : (L_BYTES + R_BYTES + P_BYTES));
     }
-};
-
-struct ImageMaps {
-    CUtensorMap L, R, P;
 };
 
 template <int LPP, int VPL, int NT, bool DT_LOAD, bool FULL>
@@ -283,9 +273,7 @@ __global__ void __launch_bounds__(NT, (NT == 256 && VPL == 1) ? HSM_TMA_MIN_BLOC
         bool mok_w, mok_s;
         bool bad = normalise_fast<LPP, VPL, FULL>(t, ln, &mok_w);
         bad |= normalise_fast<LPP, VPL, FULL>(Snext, ln, &mok_s);
-        HSM_DBG(0);
         if (__any_sync(0xffffffffu, bad)) {                        // warp-uniform, uncommon
-            HSM_DBG(1);
             Vec<VPL> uw, us;
 #pragma unroll
             for (int v = 0; v < VPL; ++v) {
@@ -296,7 +284,6 @@ __global__ void __launch_bounds__(NT, (NT == 256 && VPL == 1) ? HSM_TMA_MIN_BLOC
             const bool exact = lane_needs_exact<LPP, VPL, FULL>(uw, ln, mok_w) ||
                                lane_needs_exact<LPP, VPL, FULL>(us, ln, mok_s);
             if (__any_sync(0xffffffffu, exact)) {
-                HSM_DBG(3);
                 normalise<LPP, VPL, FULL>(uw, ln);
                 normalise<LPP, VPL, FULL>(us, ln);
                 t = uw;
@@ -322,7 +309,6 @@ __global__ void __launch_bounds__(NT, (NT == 256 && VPL == 1) ? HSM_TMA_MIN_BLOC
         for (int v = 0; v < VPL; ++v) t.q[v] = add4(add4(Xin.q[v], tn.q[v]), Din.q[v]);
         bad |= normalise_fast<LPP, VPL, FULL>(t, ln, &mok_e);
         if (__any_sync(0xffffffffu, bad)) {
-            HSM_DBG(2);
             Vec<VPL> un, ue;
 #pragma unroll
             for (int v = 0; v < VPL; ++v) un.q[v] = add4(add4(Xout.q[v], e.q[v]), Dout.q[v]);
@@ -332,7 +318,6 @@ __global__ void __launch_bounds__(NT, (NT == 256 && VPL == 1) ? HSM_TMA_MIN_BLOC
             for (int v = 0; v < VPL; ++v) ue.q[v] = add4(add4(Xin.q[v], tn.q[v]), Din.q[v]);
             exact = exact || lane_needs_exact<LPP, VPL, FULL>(ue, ln, mok_e);
             if (__any_sync(0xffffffffu, exact)) {
-                HSM_DBG(4);
                 normalise<LPP, VPL, FULL>(un, ln);
                 tn = un;
 #pragma unroll

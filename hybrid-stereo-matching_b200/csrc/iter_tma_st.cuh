@@ -212,9 +212,7 @@ __global__ void __launch_bounds__(NT, (NT == 256 && VPL == 1) ? HSM_TMA_MIN_BLOC
         bool mok_w, mok_s;
         bool bad = normalise_fast<LPP, VPL, FULL>(t, ln, &mok_w);
         bad |= normalise_fast<LPP, VPL, FULL>(Snext, ln, &mok_s);
-        HSM_DBG(0);
         if (__any_sync(0xffffffffu, bad)) {                        // warp-uniform, uncommon
-            HSM_DBG(1);
             Vec<VPL> uw, us;
 #pragma unroll
             for (int v = 0; v < VPL; ++v) {
@@ -225,7 +223,6 @@ __global__ void __launch_bounds__(NT, (NT == 256 && VPL == 1) ? HSM_TMA_MIN_BLOC
             const bool exact = lane_needs_exact<LPP, VPL, FULL>(uw, ln, mok_w) ||
                                lane_needs_exact<LPP, VPL, FULL>(us, ln, mok_s);
             if (__any_sync(0xffffffffu, exact)) {
-                HSM_DBG(3);
                 normalise<LPP, VPL, FULL>(uw, ln);
                 normalise<LPP, VPL, FULL>(us, ln);
                 t = uw;
@@ -259,7 +256,6 @@ __global__ void __launch_bounds__(NT, (NT == 256 && VPL == 1) ? HSM_TMA_MIN_BLOC
         for (int v = 0; v < VPL; ++v) t.q[v] = add4(add4(Xin.q[v], tn.q[v]), Din.q[v]);
         bad |= normalise_fast<LPP, VPL, FULL>(t, ln, &mok_e);
         if (__any_sync(0xffffffffu, bad)) {
-            HSM_DBG(2);
             Vec<VPL> un, ue;
 #pragma unroll
             for (int v = 0; v < VPL; ++v) un.q[v] = add4(add4(Xout.q[v], e.q[v]), Dout.q[v]);
@@ -269,7 +265,6 @@ __global__ void __launch_bounds__(NT, (NT == 256 && VPL == 1) ? HSM_TMA_MIN_BLOC
             for (int v = 0; v < VPL; ++v) ue.q[v] = add4(add4(Xin.q[v], tn.q[v]), Din.q[v]);
             exact = exact || lane_needs_exact<LPP, VPL, FULL>(ue, ln, mok_e);
             if (__any_sync(0xffffffffu, exact)) {
-                HSM_DBG(4);
                 normalise<LPP, VPL, FULL>(un, ln);
                 tn = un;
 #pragma unroll

@@ -1,0 +1,60 @@
+// Launch code of one iteration-kernel family (see matcher.hpp).
+#include "matcher.hpp"
+#include "iter_tma_st.cuh"
+
+namespace hsm {
+
+namespace {
+
+template <int LPP, int VPL, int NT>
+int launch_tmast(hsm_matcher *m, bool store_s, bool *launched)
+{
+    *launched = false;
+    constexpr int PX = NT / LPP, TX = PX - 2, SLOTS = NT + 2 * LPP;
+    const bool dt_load = (m->data_term == 0);
+    const size_t stage_bytes = StageLayout<LPP, VPL, NT>::stage_bytes(m->Dp, dt_load);
+    const size_t ost_bytes = ((size_t)TX * m->Dp * 4 + 127) & ~(size_t)127;
+    const size_t fixed_bytes = 6 * ost_bytes + (size_t)2 * VPL * SLOTS * 16 + 128;
+    int stages = m->stages;
+    if (stages <= 0) {
+        const int target_ctas = (NT == 256) ? (VPL == 1 ? 3 : 2) : (VPL == 1 ? 2 : 1);
+        const size_t budget = (size_t)227 * 1024 / target_ctas - 1024;
+        stages = 3;
+        while (stages > 2 && fixed_bytes + stages * stage_bytes > budget) --stages;
+    }
+    const size_t smem = fixed_bytes + (size_t)stages * stage_bytes;
+    if (smem > (size_t)227 * 1024) return HSM_OK;
+    HSM_TRY(ensure_maps(m));
+    const Geo g = geometry(m);
+    const int strips = (m->W + TX - 1) / TX;
+    IterArgs a = iter_args(m, strips, store_s);
+    const int bands = (m->ohi - m->olo + 1 + a.band_rows - 1) / a.band_rows;
+    dim3 grid(strips, bands, m->frames);
+    const bool full = (m->D == 4 * LPP * VPL);
+    const int in = m->cur, out = m->cur ^ 1;
+#define HSM_LAUNCH_TMAST(T, F)                                                                               \
+    do {                                                                                                     \
+        auto kernel = k_iter_tmast<LPP, VPL, NT, T, F>;                                                      \
+        CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
+        kernel<<<grid, NT, smem, m->stream>>>(m->tmW[in], m->tmN[in], m->tmE[in], m->tmD, m->tmI.L, m->tmI.R, \
+                                              m->tmI.P, m->tsW[out], m->tsN[out], m->tsE[out], g, a, stages);  \
+    } while (0)
+    if (full) { if (dt_load) HSM_LAUNCH_TMAST(true, true); else HSM_LAUNCH_TMAST(false, true); }
+    else { if (dt_load) HSM_LAUNCH_TMAST(true, false); else HSM_LAUNCH_TMAST(false, false); }
+#undef HSM_LAUNCH_TMAST
+    HSM_TRY(check_launch(m, "k_iter_tmast"));
+    m->stats.iteration_launches++;
+    m->cur ^= 1;
+    *launched = true;
+    return HSM_OK;
+}
+
+}  // namespace
+
+int launch_tmast_any(hsm_matcher *m, bool store_s, bool *launched)
+{
+    HSM_DISPATCH(m->cfg, { return launch_tmast<LPP, VPL, NT>(m, store_s, launched); });
+    return fail(HSM_ERR_ARG, "no lane configuration");
+}
+
+}  // namespace hsm

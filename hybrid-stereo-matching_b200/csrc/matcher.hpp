@@ -1,0 +1,122 @@
+// Internal header shared by the translation units of libhsm_b200 (not part of the C ABI).
+//
+// The library is split so that the template-heavy iteration kernels compile in parallel:
+//   hsm_api.cu       C ABI, state management, small kernels (cost volume, sweeps, readout, ...)
+//   launch_fused.cu  k_iter_fused   (algorithm 1)      launch_tma.cu    k_iter_tma   (algorithm 2)
+//   launch_tma2.cu   k_iter2_tma    (algorithm 3)      launch_ws.cu     k_iter_ws    (algorithm 4)
+//   launch_tmast.cu  k_iter_tmast   (algorithm 5, default)
+#pragma once
+
+#include "../../include/hsm.h"
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "kernels.cuh"
+
+namespace hsm {
+
+int fail(int code, const char *fmt, ...);       // records the thread-local error message, returns `code`
+
+#define CUDA_TRY(expr)                                                                            \
+    do {                                                                                          \
+        cudaError_t err__ = (expr);                                                               \
+        if (err__ != cudaSuccess)                                                                 \
+            return hsm::fail(HSM_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(err__), \
+                             __FILE__, __LINE__);                                                 \
+    } while (0)
+
+#define HSM_TRY(expr)                    \
+    do {                                 \
+        int rc__ = (expr);               \
+        if (rc__ != HSM_OK) return rc__; \
+    } while (0)
+
+// Lane configuration for a disparity range: LPP lanes per pixel, VPL float4 per lane,
+// NT threads per CTA of the fused kernels.
+struct LaneCfg {
+    int lpp, vpl, nt;
+};
+
+// Run `body` with LPP, VPL, NT as compile-time constants.
+#define HSM_DISPATCH_CASE(l, v, n, ...) \
+    if ((cfg__).lpp == l && (cfg__).vpl == v) { constexpr int LPP = l, VPL = v, NT = n; __VA_ARGS__ }
+#define HSM_DISPATCH(cfg, ...)                                  \
+    do {                                                        \
+        const hsm::LaneCfg cfg__ = (cfg);                       \
+        HSM_DISPATCH_CASE(4, 1, 256, __VA_ARGS__)               \
+        else HSM_DISPATCH_CASE(8, 1, 256, __VA_ARGS__)          \
+        else HSM_DISPATCH_CASE(16, 1, 512, __VA_ARGS__)         \
+        else HSM_DISPATCH_CASE(32, 1, 512, __VA_ARGS__)         \
+        else HSM_DISPATCH_CASE(32, 2, 512, __VA_ARGS__)         \
+        else HSM_DISPATCH_CASE(32, 4, 256, __VA_ARGS__)         \
+        else HSM_DISPATCH_CASE(4, 2, 256, __VA_ARGS__)          \
+        else HSM_DISPATCH_CASE(8, 2, 256, __VA_ARGS__)          \
+        else HSM_DISPATCH_CASE(16, 2, 512, __VA_ARGS__)         \
+    } while (0)
+
+struct ImageMaps {
+    CUtensorMap L, R, P;
+};
+
+}  // namespace hsm
+
+struct hsm_matcher {
+    int H = 0, W = 0, Wp = 0, D = 0, Dp = 0, cap = 0, device = 0;
+    hsm::LaneCfg cfg{};
+    bool ready = false;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    void *arena = nullptr;
+    size_t arena_bytes = 0;
+    float *S = nullptr, *Wm[2] = {nullptr, nullptr}, *Nm[2] = {nullptr, nullptr}, *Em[2] = {nullptr, nullptr};
+    float *Dt = nullptr;
+    float *L = nullptr, *R = nullptr;
+    int *P = nullptr;
+    char *stage[3] = {nullptr, nullptr, nullptr};
+    long long *labels = nullptr;
+    int cur = 0;          // which of the double buffers holds the current W, N, E
+    int frames = 0;       // frames of the current batch
+    bool have_fields = false, have_prior = false, dt_valid = false, s_valid = true;
+    hsm::Blend blend{hsm::kPriorNone, 0.0f, 0.0};
+    // options
+    int algorithm = 5, band_rows = 0, data_term = 1, stages = 0, lane_config = 0;
+    // TMA descriptors of the double-buffered planes (algorithm 2)
+    CUtensorMap tmW[2], tmN[2], tmE[2], tmD;
+    CUtensorMap tsW[2], tsN[2], tsE[2];          // store maps (box = TX output pixels)
+    hsm::ImageMaps tmI;
+    bool maps_valid = false;
+    int vlo = 0, vhi = 0, olo = 0, ohi = 0;
+    // statistics
+    hsm_stats stats{};
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending, pool;
+};
+
+
+namespace hsm {
+
+// shared host helpers (defined in hsm_api.cu)
+Geo geometry(const hsm_matcher *m);
+int choose_band_rows(const hsm_matcher *m, int strips);
+int check_launch(hsm_matcher *m, const char *what);
+int ensure_maps(hsm_matcher *m);
+bool tma_supported(const hsm_matcher *m);
+IterArgs iter_args(hsm_matcher *m, int strips, bool store_s);   // everything but the tensor maps
+
+// one BP iteration (or two, for algorithm 3) with the given kernel family; each lives in its own
+// translation unit.  `*launched` = false when the configuration cannot use that kernel.
+int launch_fused_any(hsm_matcher *m, bool store_s);
+int launch_tma_any(hsm_matcher *m, bool store_s);
+int launch_tma2_any(hsm_matcher *m, bool store_s, bool *launched);
+int launch_ws_any(hsm_matcher *m, bool store_s);
+int launch_tmast_any(hsm_matcher *m, bool store_s, bool *launched);
+
+}  // namespace hsm
