@@ -26,6 +26,14 @@ OPT_VALID_LO, OPT_VALID_HI, OPT_OUT_LO, OPT_OUT_HI, OPT_STAGES, OPT_LANE_CONFIG 
 PLANES = ("south", "west", "north", "east", "data")      # reference dict order, mrf.py:15-19
 
 
+class PeerInfo(ctypes.Structure):
+    _fields_ = [("ipc_handle", ctypes.c_ubyte * 64), ("off_w", ctypes.c_uint64 * 2), ("off_n", ctypes.c_uint64 * 2),
+                ("off_e", ctypes.c_uint64 * 2), ("off_mailbox", ctypes.c_uint64), ("local_base", ctypes.c_uint64),
+                ("rows", ctypes.c_int), ("cols", ctypes.c_int), ("dp", ctypes.c_int), ("out_lo", ctypes.c_int),
+                ("out_hi", ctypes.c_int), ("device", ctypes.c_int), ("current", ctypes.c_int),
+                ("reserved", ctypes.c_int)]
+
+
 class Stats(ctypes.Structure):
     _fields_ = [("kernel_launches", ctypes.c_uint64), ("iteration_launches", ctypes.c_uint64),
                 ("iterations", ctypes.c_uint64), ("iteration_ms", ctypes.c_double),
@@ -112,6 +120,10 @@ def lib():
         "hsm_halo_floats": ([vp, ctypes.POINTER(sz)], ci),
         "hsm_halo_pack": ([vp, vp, vp], ci),
         "hsm_halo_unpack": ([vp, vp, vp], ci),
+        "hsm_peer_export": ([vp, ctypes.POINTER(PeerInfo)], ci),
+        "hsm_peer_attach": ([vp, ci, ctypes.POINTER(PeerInfo), ci], ci),
+        "hsm_peer_reset": ([vp], ci),
+        "hsm_peer_detach": ([vp], ci),
         "hsm_get_stats": ([vp, ctypes.POINTER(Stats)], ci),
         "hsm_reset_stats": ([vp], ci),
         "hsm_rasterise_events": ([sz, vp, vp, vp, vp, ci, ci, ci, cd, vp, ci], ci),

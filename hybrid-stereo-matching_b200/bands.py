@@ -98,6 +98,24 @@ class CudaBandEngine(object):
             ctypes.c_void_p(from_above.data_ptr()) if from_above is not None else None,
             ctypes.c_void_p(from_below.data_ptr()) if from_below is not None else None))
 
+    # ---- fused halo exchange: the iteration kernel pushes its boundary rows into the neighbours ----
+    def peer_info(self):
+        """This band's ``hsm_peer_info`` (CUDA IPC handle + plane offsets) as a ctypes struct."""
+        info = _capi.PeerInfo()
+        _capi.check(_capi.lib().hsm_peer_export(self.matcher._handle, ctypes.byref(info)))
+        return info
+
+    def attach_peer(self, side, info, same_process=False):
+        """side 0 = the band above, 1 = the band below."""
+        _capi.check(_capi.lib().hsm_peer_attach(self.matcher._handle, int(side), ctypes.byref(info),
+                                                1 if same_process else 0))
+
+    def reset_peers(self):
+        _capi.check(_capi.lib().hsm_peer_reset(self.matcher._handle))
+
+    def detach_peers(self):
+        _capi.check(_capi.lib().hsm_peer_detach(self.matcher._handle))
+
     def labels(self):
         return self.matcher.get_map_belief()[1:self.own + 1]
 
@@ -114,9 +132,26 @@ class RowBandMatcher(object):
     and ``gather`` assembles the full map on every rank.
     """
 
-    def __init__(self, engine, rank, world, group=None):
+    def __init__(self, engine, rank, world, group=None, exchange="nccl"):
+        """``exchange``: "nccl" = pack / point-to-point send-recv / unpack after every iteration;
+        "p2p" = the iteration kernel stores its boundary rows straight into the neighbours' ghost rows
+        over NVLink (CUDA IPC mappings) and neighbours are ordered by stream-ordered flags -- no
+        collective call and no host work per iteration (``CudaBandEngine`` only)."""
         self.engine, self.rank, self.world, self.group = engine, int(rank), int(world), group
         self._send_up = self._send_down = self._recv_up = self._recv_down = None
+        self.exchange = exchange
+        self._attached = False
+
+    def _attach_neighbours(self):
+        import torch.distributed as dist
+        mine = self.engine.peer_info()
+        everyone = [None] * self.world
+        dist.all_gather_object(everyone, bytes(mine), group=self.group)
+        for side, other in ((0, self.rank - 1), (1, self.rank + 1)):
+            if 0 <= other < self.world:
+                info = _capi.PeerInfo.from_buffer_copy(everyone[other])
+                self.engine.attach_peer(side, info, same_process=False)
+        self._attached = True
 
     def _exchange(self):
         import torch.distributed as dist
@@ -141,12 +176,19 @@ class RowBandMatcher(object):
 
     def lbp(self, image_left, image_right, prior=None, prior_trust_factor=0.5,
             prior_influence_mode="const", n_iter=10):
+        p2p = self.exchange == "p2p" and self.world > 1
         with self.engine.stream_context():
             self.engine.init_fields(image_left, image_right, prior, prior_trust_factor, prior_influence_mode)
+            if p2p:
+                import torch.distributed as dist
+                if not self._attached:
+                    self._attach_neighbours()
+                self.engine.reset_peers()
+                dist.barrier(group=self.group)          # every mailbox is zero before anyone iterates
             for iteration in range(int(n_iter)):
                 last = iteration == int(n_iter) - 1
                 self.engine.iterate(finalize=last)
-                if not last and self.world > 1:
+                if not p2p and not last and self.world > 1:
                     self._exchange()
             return self.engine.labels()
 

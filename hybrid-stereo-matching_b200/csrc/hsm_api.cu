@@ -95,6 +95,7 @@ size_t arena_layout(hsm_matcher *m, bool assign)
     o = take(ib * 4); if (assign) m->P = (int *)(base + o);
     for (int i = 0; i < 3; ++i) { o = take(ib * 8); if (assign) m->stage[i] = base + o; }
     o = take(ib * 8); if (assign) m->labels = (long long *)(base + o);
+    o = take(256); if (assign) m->mailbox = (unsigned *)(base + o);
     return off;
 }
 
@@ -329,6 +330,13 @@ IterArgs iter_args(hsm_matcher *m, int strips, bool store_s)
     a.band_rows = choose_band_rows(m, strips);
     a.store_s = store_s ? 1 : 0;
     a.has_prior = m->have_prior ? 1 : 0;
+    for (int side = 0; side < 2; ++side) {
+        const hsm_matcher::Peer &p = m->peer[side];
+        a.pushW[side] = p.attached ? p.Wm[m->cur ^ 1] : nullptr;
+        a.pushN[side] = p.attached ? p.Nm[m->cur ^ 1] : nullptr;
+        a.pushE[side] = p.attached ? p.Em[m->cur ^ 1] : nullptr;
+        a.push_off[side] = p.ghost_off;
+    }
     return a;
 }
 }  // namespace hsm
@@ -406,6 +414,63 @@ float *plane_ptr(hsm_matcher *m, int which)
 }
 
 }  // namespace
+namespace {
+
+typedef CUresult (*StreamValueFn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+
+int stream_value_fns(StreamValueFn *wait_fn, StreamValueFn *write_fn)
+{
+    static StreamValueFn cached_wait = nullptr, cached_write = nullptr;
+    if (!cached_wait) {
+        void *fw = nullptr, *fr = nullptr;
+        cudaDriverEntryPointQueryResult q1, q2;
+        CUDA_TRY(cudaGetDriverEntryPoint("cuStreamWaitValue32", &fw, cudaEnableDefault, &q1));
+        CUDA_TRY(cudaGetDriverEntryPoint("cuStreamWriteValue32", &fr, cudaEnableDefault, &q2));
+        if (!fw || !fr || q1 != cudaDriverEntryPointSuccess || q2 != cudaDriverEntryPointSuccess)
+            return fail(HSM_ERR_CUDA, "driver does not provide stream memory operations");
+        cached_wait = (StreamValueFn)fw;
+        cached_write = (StreamValueFn)fr;
+    }
+    *wait_fn = cached_wait;
+    *write_fn = cached_write;
+    return HSM_OK;
+}
+
+bool p2p_active(const hsm_matcher *m) { return m->peer[0].attached || m->peer[1].attached; }
+
+// before an iteration: every attached neighbour has completed as many iterations as we have
+// (its halo rows for our next input have landed, and it no longer reads the planes we are about
+// to push into); after it: tell the neighbours.  Stream-ordered, no kernel spins.
+int p2p_before_iteration(hsm_matcher *m)
+{
+    StreamValueFn wait_fn, write_fn;
+    HSM_TRY(stream_value_fns(&wait_fn, &write_fn));
+    for (int side = 0; side < 2; ++side)
+        if (m->peer[side].attached) {
+            CUresult rc = wait_fn((CUstream)m->stream, (CUdeviceptr)(m->mailbox + side), m->p2p_iterations,
+                                  CU_STREAM_WAIT_VALUE_GEQ);
+            if (rc != CUDA_SUCCESS) return fail(HSM_ERR_CUDA, "cuStreamWaitValue32 failed with code %d", (int)rc);
+        }
+    return HSM_OK;
+}
+
+int p2p_after_iteration(hsm_matcher *m)
+{
+    StreamValueFn wait_fn, write_fn;
+    HSM_TRY(stream_value_fns(&wait_fn, &write_fn));
+    m->p2p_iterations++;
+    for (int side = 0; side < 2; ++side)
+        if (m->peer[side].attached) {
+            // default flags: a system-scope fence orders the kernel's peer stores before the flag
+            CUresult rc = write_fn((CUstream)m->stream, (CUdeviceptr)m->peer[side].mailbox, m->p2p_iterations,
+                                   CU_STREAM_WRITE_VALUE_DEFAULT);
+            if (rc != CUDA_SUCCESS) return fail(HSM_ERR_CUDA, "cuStreamWriteValue32 failed with code %d", (int)rc);
+        }
+    return HSM_OK;
+}
+
+}  // namespace
+
 extern "C" {
 
 int hsm_version(void) { return 100; }
@@ -447,6 +512,8 @@ int hsm_destroy(hsm_matcher *m)
     if (m->ready) {
         cudaSetDevice(m->device);
         cudaStreamSynchronize(m->stream);
+        for (int side = 0; side < 2; ++side)
+            if (m->peer[side].attached && m->peer[side].ipc_base) cudaIpcCloseMemHandle(m->peer[side].ipc_base);
         for (auto &pr : m->pending) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
         for (auto &pr : m->pool) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
         cudaFree(m->arena);
@@ -595,14 +662,22 @@ int hsm_iterate(hsm_matcher *m, int n_iter, int finalize)
             continue;
         }
         const int left = n_iter - it;
+        const bool p2p = p2p_active(m);
+        if (p2p) HSM_TRY(p2p_before_iteration(m));
+        struct AfterIteration {          // tell the neighbours when this iteration's launch has been queued
+            hsm_matcher *m; bool on;
+            ~AfterIteration() { if (on) p2p_after_iteration(m); }
+        } after{m, p2p};
         // algorithm 3: pairs of iterations fused in one launch; an odd count starts with a single one
-        if (m->algorithm == 3 && tma_supported(m) && m->data_term == 1 && left >= 2 && left % 2 == 0) {
+        if (!p2p && m->algorithm == 3 && tma_supported(m) && m->data_term == 1 && left >= 2 && left % 2 == 0) {
             bool launched = false;
             const bool store_s2 = finalize && left == 2;
             HSM_TRY(launch_tma2_any(m, store_s2, &launched));
             if (launched) { ++it; continue; }
         }
         const bool store_s = finalize && (it == n_iter - 1);
+        if (p2p && !(m->algorithm == 5 || m->algorithm == 2) )
+            return fail(HSM_ERR_STATE, "peer-to-peer halo push needs algorithm 2 or 5");
         if (m->algorithm == 5 && tma_supported(m)) {
             bool launched = false;
             HSM_TRY(launch_tmast_any(m, store_s, &launched));
@@ -727,6 +802,89 @@ int hsm_get_energy(hsm_matcher *m, int frame, float *out)
                                (size_t)m->H * m->W, cudaMemcpyDeviceToHost, m->stream));
     CUDA_TRY(cudaFreeAsync(scratch, m->stream));
     CUDA_TRY(cudaStreamSynchronize(m->stream));
+    return HSM_OK;
+}
+
+
+int hsm_peer_export(hsm_matcher *m, hsm_peer_info *out)
+{
+    if (!m || !out) return fail(HSM_ERR_ARG, "null argument");
+    if (m->cap != 1) return fail(HSM_ERR_ARG, "row-band mode needs capacity 1");
+    HSM_TRY(ensure_ready(m));
+    memset(out, 0, sizeof *out);
+    cudaIpcMemHandle_t handle;
+    CUDA_TRY(cudaIpcGetMemHandle(&handle, m->arena));
+    static_assert(sizeof handle <= sizeof out->ipc_handle, "ipc handle size");
+    memcpy(out->ipc_handle, &handle, sizeof handle);
+    const char *base = (const char *)m->arena;
+    for (int i = 0; i < 2; ++i) {
+        out->off_w[i] = (uint64_t)((const char *)m->Wm[i] - base);
+        out->off_n[i] = (uint64_t)((const char *)m->Nm[i] - base);
+        out->off_e[i] = (uint64_t)((const char *)m->Em[i] - base);
+    }
+    out->off_mailbox = (uint64_t)((const char *)m->mailbox - base);
+    out->local_base = (uint64_t)(uintptr_t)m->arena;
+    out->rows = m->H; out->cols = m->W; out->dp = m->Dp; out->out_lo = m->olo; out->out_hi = m->ohi;
+    out->device = m->device; out->current = m->cur;
+    return HSM_OK;
+}
+
+int hsm_peer_attach(hsm_matcher *m, int side, const hsm_peer_info *peer, int same_process)
+{
+    if (!m || !peer) return fail(HSM_ERR_ARG, "null argument");
+    if (side != 0 && side != 1) return fail(HSM_ERR_ARG, "side must be 0 (above) or 1 (below)");
+    if (m->cap != 1) return fail(HSM_ERR_ARG, "row-band mode needs capacity 1");
+    if (peer->cols != m->W || peer->dp != m->Dp) return fail(HSM_ERR_ARG, "neighbour has a different row geometry");
+    if (peer->current != m->cur) return fail(HSM_ERR_STATE, "neighbour's double buffers are out of phase");
+    HSM_TRY(ensure_ready(m));
+    hsm_matcher::Peer &p = m->peer[side];
+    if (p.attached) return fail(HSM_ERR_STATE, "side %d is already attached", side);
+    char *base = nullptr;
+    if (same_process) {
+        base = (char *)(uintptr_t)peer->local_base;
+    } else {
+        cudaIpcMemHandle_t handle;
+        memcpy(&handle, peer->ipc_handle, sizeof handle);
+        CUDA_TRY(cudaIpcOpenMemHandle(&p.ipc_base, handle, cudaIpcMemLazyEnablePeerAccess));
+        base = (char *)p.ipc_base;
+    }
+    for (int i = 0; i < 2; ++i) {
+        p.Wm[i] = (float *)(base + peer->off_w[i]);
+        p.Nm[i] = (float *)(base + peer->off_n[i]);
+        p.Em[i] = (float *)(base + peer->off_e[i]);
+    }
+    // the band above receives our first owned row in its ghost row below its last owned row, and vice versa;
+    // in its mailbox we are the neighbour on the opposite side
+    const int ghost_row = (side == 0) ? peer->out_hi + 1 : peer->out_lo - 1;
+    if (ghost_row < 0 || ghost_row >= peer->rows) return fail(HSM_ERR_ARG, "neighbour has no ghost row on that side");
+    p.ghost_off = (unsigned)ghost_row * (unsigned)m->W * (unsigned)m->Dp;
+    p.mailbox = (unsigned *)(base + peer->off_mailbox) + (1 - side);
+    p.attached = true;
+    return HSM_OK;
+}
+
+int hsm_peer_reset(hsm_matcher *m)
+{
+    if (!m) return fail(HSM_ERR_ARG, "null matcher");
+    HSM_TRY(ensure_ready(m));
+    CUDA_TRY(cudaMemsetAsync(m->mailbox, 0, 2 * sizeof(unsigned), m->stream));
+    CUDA_TRY(cudaStreamSynchronize(m->stream));
+    m->p2p_iterations = 0;
+    return HSM_OK;
+}
+
+int hsm_peer_detach(hsm_matcher *m)
+{
+    if (!m) return fail(HSM_ERR_ARG, "null matcher");
+    for (int side = 0; side < 2; ++side) {
+        hsm_matcher::Peer &p = m->peer[side];
+        if (p.attached && p.ipc_base) {
+            CUDA_TRY(cudaSetDevice(m->device));
+            CUDA_TRY(cudaStreamSynchronize(m->stream));
+            CUDA_TRY(cudaIpcCloseMemHandle(p.ipc_base));
+        }
+        p = hsm_matcher::Peer();
+    }
     return HSM_OK;
 }
 

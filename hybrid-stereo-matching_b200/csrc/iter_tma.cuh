@@ -236,6 +236,14 @@ __global__ void __launch_bounds__(NT, (NT == 256 && VPL == 1) ? HSM_TMA_MIN_BLOC
         for (int v = 0; v < VPL; ++v)
             if (FULL || ln.active[v]) st_plain(plane + off + 4 * LPP * v, val.q[v]);
     };
+    // peer-to-peer halo push: row `row` of a new plane also goes to the neighbouring GPU's ghost row
+    const unsigned lane_col = (unsigned)x * (unsigned)g.Dp + 4u * (unsigned)ln.c;
+    auto push_row = [&](float *const (&peer)[2], int row, int dx, bool mine, const Vec<VPL> &val) {
+        if (!mine) return;
+        const unsigned col = lane_col + (unsigned)(dx * g.Dp);
+        if (row == a.olo && peer[0] != nullptr) store_at(peer[0], a.push_off[0] + col, val);
+        if (row == a.ohi && peer[1] != nullptr) store_at(peer[1], a.push_off[1] + col, val);
+    };
 
     // row yb0-1 only contributes S'(yb0)
     {
@@ -293,6 +301,7 @@ __global__ void __launch_bounds__(NT, (NT == 256 && VPL == 1) ? HSM_TMA_MIN_BLOC
 #pragma unroll
         for (int v = 0; v < VPL; ++v) ex(par, v, tid) = t.q[v];
         if (st_w && y <= yb1) store_at(Wout, row_off - (unsigned)g.Dp, t);
+        push_row(a.pushW, y, -1, st_w && y <= yb1, t);
         if (STORE_S && st_n && y + 1 <= yb1) store_at(Sout, row_off + row_stride, Snext);
         __syncthreads();                       // the row's only CTA barrier: W' published, stage consumed
         refill(y - yb0 + 1);
@@ -329,6 +338,10 @@ __global__ void __launch_bounds__(NT, (NT == 256 && VPL == 1) ? HSM_TMA_MIN_BLOC
         const bool upper = (y > yb0);          // row y-1 belongs to this band
         if (upper && st_n) store_at(Nout, row_off - row_stride, tn);
         if (upper && st_e) store_at(Eout, row_off - row_stride + (unsigned)g.Dp, t);
+        if (upper) {
+            push_row(a.pushN, y - 1, 0, st_n, tn);
+            push_row(a.pushE, y - 1, +1, st_e, t);
+        }
         row_off += row_stride;
     };
 

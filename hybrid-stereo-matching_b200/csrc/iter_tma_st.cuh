@@ -175,6 +175,15 @@ __global__ void __launch_bounds__(NT, (NT == 256 && VPL == 1) ? HSM_TMA_MIN_BLOC
         for (int v = 0; v < VPL; ++v)
             if (FULL || ln.active[v]) st_plain(plane + off + 4 * LPP * v, val.q[v]);
     };
+    // peer-to-peer halo push: row `row` of a new plane also goes to the neighbouring GPU's ghost row
+    // (plain stores through the peer mapping; the TMA store maps only cover this GPU's planes)
+    const unsigned lane_col = (unsigned)x * (unsigned)g.Dp + 4u * (unsigned)ln.c;
+    auto push_row = [&](float *const (&peer)[2], int row, int dx, bool mine, const Vec<VPL> &val) {
+        if (!mine) return;
+        const unsigned col = lane_col + (unsigned)(dx * g.Dp);
+        if (row == a.olo && peer[0] != nullptr) store_at(peer[0], a.push_off[0] + col, val);
+        if (row == a.ohi && peer[1] != nullptr) store_at(peer[1], a.push_off[1] + col, val);
+    };
 
     // row yb0-1 only contributes S'(yb0)
     {
@@ -232,6 +241,7 @@ __global__ void __launch_bounds__(NT, (NT == 256 && VPL == 1) ? HSM_TMA_MIN_BLOC
 #pragma unroll
         for (int v = 0; v < VPL; ++v) ex(par, v, tid) = t.q[v];
         if (st_w) stage_out(st_wp, par, t);
+        push_row(a.pushW, y, -1, st_w && (x - 1) < g.W && y <= yb1, t);
         if (STORE_S && st_s && y + 1 <= yb1) store_at(Sout, row_off + row_stride, Snext);
         // staging writes (this row's W', the previous row's N', E') -> visible to the async proxy
         tma_store_fence();
@@ -277,6 +287,8 @@ __global__ void __launch_bounds__(NT, (NT == 256 && VPL == 1) ? HSM_TMA_MIN_BLOC
         if (upper) {
             if (st_n) stage_out(st_np, par, tn);
             if (st_e) stage_out(st_ep, par, t);
+            push_row(a.pushN, y - 1, 0, st_n && in_x, tn);
+            push_row(a.pushE, y - 1, +1, st_e && (x + 1) < g.W, t);
         }
         row_off += row_stride;
     };

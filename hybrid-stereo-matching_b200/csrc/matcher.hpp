@@ -95,6 +95,16 @@ struct hsm_matcher {
     hsm::ImageMaps tmI;
     bool maps_valid = false;
     int vlo = 0, vhi = 0, olo = 0, ohi = 0;
+    // row-band mode with peer-to-peer halo push (hsm_peer_*): side 0 = band above, 1 = band below
+    struct Peer {
+        bool attached = false;
+        void *ipc_base = nullptr;                // mapping opened with cudaIpcOpenMemHandle (null if same process)
+        float *Wm[2] = {nullptr, nullptr}, *Nm[2] = {nullptr, nullptr}, *Em[2] = {nullptr, nullptr};
+        unsigned *mailbox = nullptr;             // the slot of the neighbour's mailbox this matcher writes
+        unsigned ghost_off = 0;                  // element offset of the neighbour's ghost row inside its planes
+    } peer[2];
+    unsigned *mailbox = nullptr;                 // [0] written by the band above, [1] by the band below
+    unsigned p2p_iterations = 0;                 // iterations completed since hsm_peer_reset
     // statistics
     hsm_stats stats{};
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending, pool;

@@ -162,6 +162,28 @@ int hsm_halo_floats(hsm_matcher *m, size_t *count);
 int hsm_halo_pack(hsm_matcher *m, float *top, float *bottom);
 int hsm_halo_unpack(hsm_matcher *m, const float *from_above, const float *from_below);
 
+/*
+ * Row-band mode, fused variant: instead of pack -> NCCL -> unpack, the iteration kernel itself
+ * stores its first / last owned row of the new W, N, E into the neighbouring GPU's ghost rows
+ * through peer-mapped memory (NVLink), and iterations are ordered between neighbours with
+ * stream-ordered flag writes / waits (cuStreamWriteValue32 / cuStreamWaitValue32) on a mailbox in
+ * each matcher's arena -- no collective call and no host round trip per iteration.
+ *   hsm_peer_export: fills `out` (CUDA IPC handle of the arena + plane offsets); send it to the neighbours.
+ *   hsm_peer_attach: side 0 = the band above, 1 = the band below; same_process != 0 uses the address
+ *                    directly (two matchers in one process, e.g. tests on a single GPU).
+ *   hsm_peer_reset:  zero the iteration counters; every rank calls it after hsm_init_fields and
+ *                    synchronises with its neighbours (any host barrier) before the first hsm_iterate.
+ */
+typedef struct hsm_peer_info {
+    unsigned char ipc_handle[64];
+    uint64_t off_w[2], off_n[2], off_e[2], off_mailbox, local_base;
+    int rows, cols, dp, out_lo, out_hi, device, current, reserved;
+} hsm_peer_info;
+int hsm_peer_export(hsm_matcher *m, hsm_peer_info *out);
+int hsm_peer_attach(hsm_matcher *m, int side, const hsm_peer_info *peer, int same_process);
+int hsm_peer_reset(hsm_matcher *m);
+int hsm_peer_detach(hsm_matcher *m);
+
 int hsm_get_stats(hsm_matcher *m, hsm_stats *out);
 int hsm_reset_stats(hsm_matcher *m);
 

@@ -53,3 +53,49 @@ def test_cuda_band_engines_match_unbanded(hsm, world, shape, n_iter):
         first, last_row = bands.band_bounds(rows, world, r)
         for name, plane in e.planes().items():
             assert np.array_equal(plane, want_planes[name][:, first:last_row + 1, :]), (r, name)
+
+
+@pytest.mark.parametrize("world,shape,n_iter,levels_algo", [(2, (21, 50), 6, (12, 5)), (3, (20, 70), 5, (32, 5)),
+                                                            (3, (12, 230), 4, (200, 2))])
+def test_fused_peer_push_matches_unbanded(hsm, world, shape, n_iter, levels_algo):
+    """The fused halo exchange on ONE GPU: the band engines live in one process, attach to each other by
+    address and their iteration kernels push boundary rows into each other's ghost rows; ordering comes
+    from stream-ordered flag waits (no spinning kernels, so two streams on one GPU cannot deadlock)."""
+    import torch
+    from importlib import import_module
+    bands = import_module("hybrid-stereo-matching_b200.bands")
+    synth = import_module("hybrid-stereo-matching_b200.synth")
+    capi = import_module("hybrid-stereo-matching_b200._capi")
+    rows, cols = shape
+    levels, algorithm = levels_algo
+    left, right, disparity = synth.textured_pair(rows, cols, levels, 19, block=(5, 6))
+    prior = synth.sparse_prior(disparity, levels, 19, density=0.2)
+    want = mrf_c.OracleMRFC((rows, cols), levels)
+    want_labels = want.lbp(left, right, prior, prior_trust_factor=1.0, prior_influence_mode="adaptive", n_iter=n_iter)
+
+    engines = [bands.CudaBandEngine(rows, cols, levels, *bands.band_bounds(rows, world, r)) for r in range(world)]
+    for e in engines:
+        e.matcher.set_option(capi.OPT_ALGORITHM, algorithm)
+        with e.stream_context():
+            e.init_fields(left, right, prior, 1.0, "adaptive")
+    infos = [e.peer_info() for e in engines]
+    for r, e in enumerate(engines):
+        if r > 0:
+            e.attach_peer(0, infos[r - 1], same_process=True)
+        if r < world - 1:
+            e.attach_peer(1, infos[r + 1], same_process=True)
+        e.reset_peers()
+    torch.cuda.synchronize()
+    for it in range(n_iter):                       # every rank queues its iteration; flags order them on the device
+        for e in engines:
+            with e.stream_context():
+                e.iterate(finalize=(it == n_iter - 1))
+    torch.cuda.synchronize()
+    got = np.concatenate([e.labels() for e in engines], axis=0)
+    assert np.array_equal(got, want_labels)
+    want_planes = want._message_field
+    for r, e in enumerate(engines):
+        first, last_row = bands.band_bounds(rows, world, r)
+        for name, plane in e.planes().items():
+            assert np.array_equal(plane, want_planes[name][:, first:last_row + 1, :]), (r, name)
+        e.detach_peers()

@@ -19,7 +19,8 @@ left, right, disparity = synth.textured_pair(rows, cols, levels, 4321)
 prior = synth.sparse_prior(disparity, levels, 4321)
 first, last = bands.band_bounds(rows, world, rank)
 engine = bands.CudaBandEngine(rows, cols, levels, first, last, device=local)
-matcher = bands.RowBandMatcher(engine, rank, world)
+exchange = os.environ.get("HSM_EXCHANGE", "nccl")
+matcher = bands.RowBandMatcher(engine, rank, world, exchange=exchange)
 kw = dict(prior_trust_factor=1.0, prior_influence_mode="adaptive", n_iter=n_iter)
 matcher.lbp(left, right, prior, **kw)                                  # warm-up
 torch.cuda.synchronize()
@@ -31,13 +32,44 @@ torch.cuda.synchronize()
 if world > 1:
     dist.barrier()
 elapsed = time.perf_counter() - t0
+# iteration loop only (no init / readout): time n_iter iterations with their halo exchanges
+engine.init_fields(left, right, prior, 1.0, "adaptive")
+torch.cuda.synchronize()
+if world > 1:
+    dist.barrier()
+t2 = time.perf_counter()
+if exchange == "p2p" and world > 1:
+    engine.reset_peers()
+    dist.barrier()
+    t2 = time.perf_counter()
+with engine.stream_context():
+    for it in range(n_iter):
+        engine.iterate(finalize=(it == n_iter - 1))
+        if exchange != "p2p" and it < n_iter - 1 and world > 1:
+            matcher._exchange()
+torch.cuda.synchronize()
+if world > 1:
+    dist.barrier()
+loop_s = time.perf_counter() - t2
+# the same without any exchange (wrong results, timing only): what the exchange costs
+if exchange == "p2p" and world > 1:
+    engine.detach_peers(); matcher._attached = False
+t3 = time.perf_counter()
+with engine.stream_context():
+    for it in range(n_iter):
+        engine.iterate(finalize=(it == n_iter - 1))
+torch.cuda.synchronize()
+if world > 1:
+    dist.barrier()
+noex_s = time.perf_counter() - t3
 full = matcher.gather(local_labels)
 if rank == 0:
     ref = hsm.StereoMRF((rows, cols), levels, device=local)
     t1 = time.perf_counter()
     want = ref.lbp(left, right, prior, **kw)
     single = time.perf_counter() - t1
-    print(json.dumps({"shape": [rows, cols, levels], "n_iter": n_iter, "world": world, "band_s": round(elapsed, 4),
+    print(json.dumps({"exchange": exchange, "shape": [rows, cols, levels], "n_iter": n_iter, "world": world, "band_s": round(elapsed, 4), "iter_ms_with_exchange": round(1e3 * loop_s / n_iter, 4),
+                      "iter_ms_without_exchange": round(1e3 * noex_s / n_iter, 4),
                       "single_gpu_s_incl_init": round(single, 4), "identical_to_single_gpu": bool(np.array_equal(full, want))}))
 if world > 1:
     dist.destroy_process_group()
