@@ -784,7 +784,7 @@ int hsm_get_energy(hsm_matcher *m, int frame, float *out)
     if (!m->s_valid) return fail(HSM_ERR_STATE, "south plane is stale: last hsm_iterate was not finalized");
     HSM_TRY(ensure_ready(m));
     HSM_TRY(ensure_data_plane(m));
-    // the staging area doubles as scratch for one frame's energy (needs H*W*Dp*4 <= 3*cap*H*W*8 -> Dp <= 6*cap)
+    // stream-ordered scratch for the energy planes of the current batch
     float *scratch = nullptr;
     const size_t need = (size_t)m->frames * m->H * m->W * m->Dp * sizeof(float);
     CUDA_TRY(cudaMallocAsync((void **)&scratch, need, m->stream));
