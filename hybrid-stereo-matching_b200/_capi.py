@@ -64,6 +64,7 @@ def build_library(force=False, verbose=False, jobs=None):
     obj_dir = os.path.join(_PKG_DIR, "build")
     os.makedirs(obj_dir, exist_ok=True)
     compile_flags = [flag for flag in NVCC_FLAGS if flag != "-shared"] + (["-Xptxas", "-v"] if verbose else [])
+    compile_flags += os.environ.get("HSM_NVCC_EXTRA", "").split()          # development: e.g. -DHSM_STORE_POLICY=1
 
     def compile_unit(unit):
         obj = os.path.join(obj_dir, unit[:-3] + ".o")

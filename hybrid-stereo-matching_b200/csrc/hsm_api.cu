@@ -680,13 +680,13 @@ int hsm_iterate(hsm_matcher *m, int n_iter, int finalize)
             return fail(HSM_ERR_STATE, "peer-to-peer halo push needs algorithm 2 or 5");
         if (m->algorithm == 5 && tma_supported(m)) {
             bool launched = false;
-            HSM_TRY(launch_tmast_any(m, store_s, &launched));
+            HSM_TRY(p2p ? launch_tmast_push_any(m, store_s, &launched) : launch_tmast_any(m, store_s, &launched));
             if (launched) continue;
         }
         if (m->algorithm == 4 && tma_supported(m))
             HSM_TRY(launch_ws_any(m, store_s));
         else if (m->algorithm >= 2 && tma_supported(m))
-            HSM_TRY(launch_tma_any(m, store_s));
+            HSM_TRY(p2p ? launch_tma_push_any(m, store_s) : launch_tma_any(m, store_s));
         else
             HSM_TRY(launch_fused_any(m, store_s));
     }

@@ -98,7 +98,7 @@ struct StageLayout {
     }
 };
 
-template <int LPP, int VPL, int NT, bool DT_LOAD, bool FULL>
+template <int LPP, int VPL, int NT, bool DT_LOAD, bool FULL, bool PUSH>
 __global__ void __launch_bounds__(NT, (NT == 256 && VPL == 1) ? HSM_TMA_MIN_BLOCKS : 1)
     k_iter_tma(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmN,
                const __grid_constant__ CUtensorMap tmE, const __grid_constant__ CUtensorMap tmD,
@@ -278,7 +278,7 @@ __global__ void __launch_bounds__(NT, (NT == 256 && VPL == 1) ? HSM_TMA_MIN_BLOC
             t.q[v] = sum4(Sin.q[v], n.q[v], e.q[v], Dout.q[v]);
             Snext.q[v] = sum4(w.q[v], n.q[v], e.q[v], Dout.q[v]);
         }
-        bool mok_w, mok_s;
+        float mok_w, mok_s;
         bool bad = normalise_fast<LPP, VPL, FULL>(t, ln, &mok_w);
         bad |= normalise_fast<LPP, VPL, FULL>(Snext, ln, &mok_s);
         if (__any_sync(0xffffffffu, bad)) {                        // warp-uniform, uncommon
@@ -301,7 +301,7 @@ __global__ void __launch_bounds__(NT, (NT == 256 && VPL == 1) ? HSM_TMA_MIN_BLOC
 #pragma unroll
         for (int v = 0; v < VPL; ++v) ex(par, v, tid) = t.q[v];
         if (st_w && y <= yb1) store_at(Wout, row_off - (unsigned)g.Dp, t);
-        push_row(a.pushW, y, -1, st_w && y <= yb1, t);
+        if constexpr (PUSH) push_row(a.pushW, y, -1, st_w && y <= yb1, t);
         if (STORE_S && st_n && y + 1 <= yb1) store_at(Sout, row_off + row_stride, Snext);
         __syncthreads();                       // the row's only CTA barrier: W' published, stage consumed
         refill(y - yb0 + 1);
@@ -312,7 +312,7 @@ __global__ void __launch_bounds__(NT, (NT == 256 && VPL == 1) ? HSM_TMA_MIN_BLOC
         Vec<VPL> tn;
 #pragma unroll
         for (int v = 0; v < VPL; ++v) tn.q[v] = add4(add4(Xout.q[v], e.q[v]), Dout.q[v]);
-        bool mok_n, mok_e;
+        float mok_n, mok_e;
         bad = normalise_fast<LPP, VPL, FULL>(tn, ln, &mok_n);
 #pragma unroll
         for (int v = 0; v < VPL; ++v) t.q[v] = add4(add4(Xin.q[v], tn.q[v]), Din.q[v]);
@@ -339,8 +339,8 @@ __global__ void __launch_bounds__(NT, (NT == 256 && VPL == 1) ? HSM_TMA_MIN_BLOC
         if (upper && st_n) store_at(Nout, row_off - row_stride, tn);
         if (upper && st_e) store_at(Eout, row_off - row_stride + (unsigned)g.Dp, t);
         if (upper) {
-            push_row(a.pushN, y - 1, 0, st_n, tn);
-            push_row(a.pushE, y - 1, +1, st_e, t);
+            if constexpr (PUSH) push_row(a.pushN, y - 1, 0, st_n, tn);
+            if constexpr (PUSH) push_row(a.pushE, y - 1, +1, st_e, t);
         }
         row_off += row_stride;
     };

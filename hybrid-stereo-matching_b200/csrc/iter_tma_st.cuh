@@ -18,7 +18,7 @@ __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_fence() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-template <int LPP, int VPL, int NT, bool DT_LOAD, bool FULL>
+template <int LPP, int VPL, int NT, bool DT_LOAD, bool FULL, bool PUSH>
 __global__ void __launch_bounds__(NT, (NT == 256 && VPL == 1) ? HSM_TMA_MIN_BLOCKS : 1)
     k_iter_tmast(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmN,
                const __grid_constant__ CUtensorMap tmE, const __grid_constant__ CUtensorMap tmD,
@@ -218,7 +218,7 @@ __global__ void __launch_bounds__(NT, (NT == 256 && VPL == 1) ? HSM_TMA_MIN_BLOC
             t.q[v] = sum4(Sin.q[v], n.q[v], e.q[v], Dout.q[v]);
             Snext.q[v] = sum4(w.q[v], n.q[v], e.q[v], Dout.q[v]);
         }
-        bool mok_w, mok_s;
+        float mok_w, mok_s;
         bool bad = normalise_fast<LPP, VPL, FULL>(t, ln, &mok_w);
         bad |= normalise_fast<LPP, VPL, FULL>(Snext, ln, &mok_s);
         if (__any_sync(0xffffffffu, bad)) {                        // warp-uniform, uncommon
@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(NT, (NT == 256 && VPL == 1) ? HSM_TMA_MIN_BLOC
 #pragma unroll
         for (int v = 0; v < VPL; ++v) ex(par, v, tid) = t.q[v];
         if (st_w) stage_out(st_wp, par, t);
-        push_row(a.pushW, y, -1, st_w && (x - 1) < g.W && y <= yb1, t);
+        if constexpr (PUSH) push_row(a.pushW, y, -1, st_w && (x - 1) < g.W && y <= yb1, t);
         if (STORE_S && st_s && y + 1 <= yb1) store_at(Sout, row_off + row_stride, Snext);
         // staging writes (this row's W', the previous row's N', E') -> visible to the async proxy
         tma_store_fence();
@@ -260,7 +260,7 @@ __global__ void __launch_bounds__(NT, (NT == 256 && VPL == 1) ? HSM_TMA_MIN_BLOC
         Vec<VPL> tn;
 #pragma unroll
         for (int v = 0; v < VPL; ++v) tn.q[v] = add4(add4(Xout.q[v], e.q[v]), Dout.q[v]);
-        bool mok_n, mok_e;
+        float mok_n, mok_e;
         bad = normalise_fast<LPP, VPL, FULL>(tn, ln, &mok_n);
 #pragma unroll
         for (int v = 0; v < VPL; ++v) t.q[v] = add4(add4(Xin.q[v], tn.q[v]), Din.q[v]);
@@ -287,8 +287,8 @@ __global__ void __launch_bounds__(NT, (NT == 256 && VPL == 1) ? HSM_TMA_MIN_BLOC
         if (upper) {
             if (st_n) stage_out(st_np, par, tn);
             if (st_e) stage_out(st_ep, par, t);
-            push_row(a.pushN, y - 1, 0, st_n && in_x, tn);
-            push_row(a.pushE, y - 1, +1, st_e && (x + 1) < g.W, t);
+            if constexpr (PUSH) push_row(a.pushN, y - 1, 0, st_n && in_x, tn);
+            if constexpr (PUSH) push_row(a.pushE, y - 1, +1, st_e && (x + 1) < g.W, t);
         }
         row_off += row_stride;
     };

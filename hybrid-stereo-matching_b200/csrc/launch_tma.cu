@@ -1,4 +1,10 @@
 // Launch code of one iteration-kernel family (see matcher.hpp).
+// Compiled twice: as is (no peers attached: the halo-push code is compiled out of the kernels), and
+// through launch_tma_push.cu with HSM_PUSH = true for row bands with peer-to-peer halo push.
+#ifndef HSM_PUSH
+#define HSM_PUSH false
+#define HSM_TMA_ENTRY launch_tma_any
+#endif
 #include "matcher.hpp"
 #include "iter_tma.cuh"
 
@@ -33,7 +39,7 @@ int launch_tma(hsm_matcher *m, bool store_s)
     const CUtensorMap &tw = m->tmW[m->cur], &tn = m->tmN[m->cur], &te = m->tmE[m->cur], &td = m->tmD;
 #define HSM_LAUNCH_TMA(T, F)                                                                                 \
     do {                                                                                                     \
-        auto kernel = k_iter_tma<LPP, VPL, NT, T, F>;                                                        \
+        auto kernel = k_iter_tma<LPP, VPL, NT, T, F, HSM_PUSH>;                                                        \
         CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
         kernel<<<grid, NT, smem, m->stream>>>(tw, tn, te, td, m->tmI.L, m->tmI.R, m->tmI.P, g, a, stages);                         \
     } while (0)
@@ -50,7 +56,7 @@ int launch_tma(hsm_matcher *m, bool store_s)
 // configuration cannot use it (caller falls back to one iteration per launch).
 }  // namespace
 
-int launch_tma_any(hsm_matcher *m, bool store_s)
+int HSM_TMA_ENTRY(hsm_matcher *m, bool store_s)
 {
     HSM_DISPATCH(m->cfg, { return launch_tma<LPP, VPL, NT>(m, store_s); });
     return fail(HSM_ERR_ARG, "no lane configuration");

@@ -1,4 +1,10 @@
 // Launch code of one iteration-kernel family (see matcher.hpp).
+// Compiled twice: as is (no peers attached: the halo-push code is compiled out of the kernels), and
+// through launch_tmast_push.cu with HSM_PUSH = true for row bands with peer-to-peer halo push.
+#ifndef HSM_PUSH
+#define HSM_PUSH false
+#define HSM_TMAST_ENTRY launch_tmast_any
+#endif
 #include "matcher.hpp"
 #include "iter_tma_st.cuh"
 
@@ -34,7 +40,7 @@ int launch_tmast(hsm_matcher *m, bool store_s, bool *launched)
     const int in = m->cur, out = m->cur ^ 1;
 #define HSM_LAUNCH_TMAST(T, F)                                                                               \
     do {                                                                                                     \
-        auto kernel = k_iter_tmast<LPP, VPL, NT, T, F>;                                                      \
+        auto kernel = k_iter_tmast<LPP, VPL, NT, T, F, HSM_PUSH>;                                                      \
         CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
         kernel<<<grid, NT, smem, m->stream>>>(m->tmW[in], m->tmN[in], m->tmE[in], m->tmD, m->tmI.L, m->tmI.R, \
                                               m->tmI.P, m->tsW[out], m->tsN[out], m->tsE[out], g, a, stages);  \
@@ -51,7 +57,7 @@ int launch_tmast(hsm_matcher *m, bool store_s, bool *launched)
 
 }  // namespace
 
-int launch_tmast_any(hsm_matcher *m, bool store_s, bool *launched)
+int HSM_TMAST_ENTRY(hsm_matcher *m, bool store_s, bool *launched)
 {
     HSM_DISPATCH(m->cfg, { return launch_tmast<LPP, VPL, NT>(m, store_s, launched); });
     return fail(HSM_ERR_ARG, "no lane configuration");

@@ -125,8 +125,10 @@ IterArgs iter_args(hsm_matcher *m, int strips, bool store_s);   // everything bu
 // translation unit.  `*launched` = false when the configuration cannot use that kernel.
 int launch_fused_any(hsm_matcher *m, bool store_s);
 int launch_tma_any(hsm_matcher *m, bool store_s);
+int launch_tma_push_any(hsm_matcher *m, bool store_s);                 // same, halo push compiled in
 int launch_tma2_any(hsm_matcher *m, bool store_s, bool *launched);
 int launch_ws_any(hsm_matcher *m, bool store_s);
 int launch_tmast_any(hsm_matcher *m, bool store_s, bool *launched);
+int launch_tmast_push_any(hsm_matcher *m, bool store_s, bool *launched);
 
 }  // namespace hsm
