@@ -14,8 +14,9 @@ Printed JSON (rank 0, one line):
           dtypes) already resident in HBM, labels (int64) left in HBM; CUDA events, max over ranks.
   e2e     the same metric through the public API (StereoMRF.lbp_batch) with HOST buffers: H2D of the
           inputs and D2H of the labels inside the timed region.
-  roofline  message kernel: algorithmic bytes per launch (24 B x H x W x D x frames) / measured launch
-          time (CUDA events on the launching stream) against the measured HBM peak.
+  roofline  message kernel: algorithmic bytes per iteration (24 B x H x W x D x frames; an iteration is
+          two concurrent launches, one per half of the frames, that share the HBM) / measured device
+          time per iteration (CUDA events on the launching stream) against the measured HBM peak.
   cpu_baseline  the numpy oracle (a restatement of the reference's numpy code) on the host, one process.
 
 --impl reference times the reference's CPU algorithm (the oracle port; the reference is Python 2 and
@@ -288,9 +289,14 @@ def main():
     if rank == 0:
         peak, peak_source = measured_peak()
         launches = stats["iteration_launches"]
+        iterations = max(stats["iterations"], 1)
+        # One BP iteration over a chunk of `cap` frames is launched as `per_iter` concurrent kernels (frame
+        # groups on two streams, each filling the other's tail); they share the HBM, so the roofline unit is
+        # the iteration: combined algorithmic bytes of its launches / the iteration's device time.
+        per_iter = max(int(round(launches / iterations)), 1)
         frames_per_launch = cap if frames % cap == 0 else frames / len(chunks)
         algo_bytes = 24.0 * ROWS * COLS * LEVELS * frames_per_launch
-        launch_ms = stats["iteration_ms"] / max(launches, 1)
+        launch_ms = stats["iteration_ms"] / iterations
         achieved = algo_bytes / (launch_ms * 1e-3) / 1e9
         traffic = recorded_traffic()
         line = {
@@ -308,11 +314,14 @@ def main():
                     "d2h_bytes_per_step": int(h_out.nbytes), "timing": "wall clock between device synchronisations",
                     "labels_equal_device_arm": same},
             "gpu_launches": int(stats["kernel_launches"]),
-            "roofline": {"bound": "hbm", "kernel": "k_iter_tmast (fused 4-sweep BP iteration, TMA loads + TMA stores)",
+            "roofline": {"bound": "hbm", "kernel": "k_iter_tmast (fused 4-sweep BP iteration, TMA loads + TMA stores); "
+                                                    "unit = one iteration over frames_per_launch frames",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "peak_source": peak_source, "algorithmic_bytes_per_launch": algo_bytes,
                          "launch_ms": launch_ms, "launches_timed": int(launches),
-                         "traffic": None if not traffic else traffic.get("dram_bytes_per_launch"),
+                         "concurrent_launches_per_iteration": per_iter,
+                         "traffic": None if not traffic else
+                         traffic["dram_bytes_per_launch"] * frames_per_launch / traffic["frames_per_launch"],
                          "traffic_source": None if not traffic else traffic.get("source")},
             "clocks": clocks.summary(),
         }

@@ -81,8 +81,8 @@ class CudaBandEngine(object):
         self.matcher._init_fields(self._local(image_left), self._local(image_right), local_prior,
                                   prior_trust_factor, prior_influence_mode, True)
 
-    def iterate(self, finalize):
-        _capi.check(_capi.lib().hsm_iterate(self.matcher._handle, 1, 1 if finalize else 0))
+    def iterate(self, finalize, n_iter=1):
+        _capi.check(_capi.lib().hsm_iterate(self.matcher._handle, int(n_iter), 1 if finalize else 0))
 
     def new_halo(self):
         return self.torch.empty(self.halo_floats, dtype=self.torch.float32, device=self.device)
@@ -185,10 +185,15 @@ class RowBandMatcher(object):
                     self._attach_neighbours()
                 self.engine.reset_peers()
                 dist.barrier(group=self.group)          # every mailbox is zero before anyone iterates
+            if p2p or self.world == 1:
+                # no host work between iterations: the whole loop is queued by one native call
+                if int(n_iter) > 0:
+                    self.engine.iterate(finalize=True, n_iter=n_iter)
+                return self.engine.labels()
             for iteration in range(int(n_iter)):
                 last = iteration == int(n_iter) - 1
                 self.engine.iterate(finalize=last)
-                if not p2p and not last and self.world > 1:
+                if not last:
                     self._exchange()
             return self.engine.labels()
 

@@ -235,18 +235,23 @@ int load_prior(hsm_matcher *m, const void *src, int dtype, size_t n, int on_devi
 }  // namespace
 
 namespace hsm {
-int choose_band_rows(const hsm_matcher *m, int strips)
+int choose_band_rows(const hsm_matcher *m, int strips, int ctas_per_sm)
 {
     const int rows = m->ohi - m->olo + 1;
     if (m->band_rows > 0) return std::min(m->band_rows, rows);
-    // Aim for ~16 CTAs per SM over the whole launch (several waves, short tail).  Every band re-reads
-    // two halo rows, so bands are normally at least 12 rows; when even 12-row bands cannot fill the
-    // machine once (a single small frame: latency-, not bandwidth-bound) they may shrink to 4 rows.
+    // Every band re-reads two halo rows (cost 2 / band_rows) and a CTA's life is one band, so the machine
+    // drains for about half a band at the end of a launch.  Measured optimum (tools/band_sweep.py): about
+    // 6 resident-CTA waves per launch when an iteration is one kernel, about 4 over both kernels when the
+    // frames run as two concurrent groups (the other group fills the drain, so bands can be taller);
+    // beyond ~64 rows the halo saving is below 3 % and taller bands only lengthen the drain.
+    // Bands are normally at least 12 rows; when even 12-row bands cannot fill the machine once (a single
+    // small frame: latency-, not bandwidth-bound) they may shrink to 4 rows.
     const long per_band = (long)strips * m->frames;
     int min_rows = 12;
     while (min_rows > 4 && per_band * ((rows + min_rows - 1) / min_rows) < 148L * 3) min_rows -= 2;
-    const long target = 148L * 16;
-    long bands = (target + per_band - 1) / per_band;
+    const bool grouped = m->launch_frames < m->frames;
+    const long target = 148L * std::max(1, ctas_per_sm) * (grouped ? 4 : 6);
+    long bands = std::max((target + per_band - 1) / per_band, (long)(rows + 63) / 64);
     bands = std::max(1L, std::min<long>(bands, std::max(1, rows / min_rows)));
     return (int)((rows + bands - 1) / bands);
 }
@@ -318,7 +323,7 @@ int make_image_map(const hsm_matcher *m, CUtensorMap *map, void *image, bool is_
 namespace hsm {
 bool tma_supported(const hsm_matcher *m) { return m->Dp <= 256 && m->cfg.lpp * m->cfg.vpl * 4 <= 256; }
 
-IterArgs iter_args(hsm_matcher *m, int strips, bool store_s)
+IterArgs iter_args(hsm_matcher *m, int strips, bool store_s, int ctas_per_sm)
 {
     IterArgs a;
     a.Win = m->Wm[m->cur]; a.Nin = m->Nm[m->cur]; a.Ein = m->Em[m->cur];
@@ -327,9 +332,10 @@ IterArgs iter_args(hsm_matcher *m, int strips, bool store_s)
     a.Dt = m->Dt; a.L = m->L; a.R = m->R; a.P = m->have_prior ? m->P : nullptr;
     a.blend = m->blend;
     a.olo = m->olo; a.ohi = m->ohi;
-    a.band_rows = choose_band_rows(m, strips);
+    a.band_rows = choose_band_rows(m, strips, ctas_per_sm);
     a.store_s = store_s ? 1 : 0;
     a.has_prior = m->have_prior ? 1 : 0;
+    a.frame0 = m->launch_frame0;
     for (int side = 0; side < 2; ++side) {
         const hsm_matcher::Peer &p = m->peer[side];
         a.pushW[side] = p.attached ? p.Wm[m->cur ^ 1] : nullptr;
@@ -517,6 +523,9 @@ int hsm_destroy(hsm_matcher *m)
         for (auto &pr : m->pending) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
         for (auto &pr : m->pool) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
         cudaFree(m->arena);
+        if (m->aux_stream) cudaStreamDestroy(m->aux_stream);
+        if (m->fork_event) cudaEventDestroy(m->fork_event);
+        if (m->join_event) cudaEventDestroy(m->join_event);
         if (m->own_stream) cudaStreamDestroy(m->stream);
     }
     delete m;
@@ -572,6 +581,9 @@ int hsm_set_option(hsm_matcher *m, int key, int value)
         case HSM_OPT_STAGES:
             if (value < 0 || value > 8 || value == 1) return fail(HSM_ERR_ARG, "stages must be 0 (auto) or 2..8");
             m->stages = value; return HSM_OK;
+        case HSM_OPT_FRAME_GROUPS:
+            if (value < 0 || value > 2) return fail(HSM_ERR_ARG, "frame groups must be 0 (auto), 1 or 2");
+            m->frame_groups = value; return HSM_OK;
         default: return fail(HSM_ERR_ARG, "unknown option %d", key);
     }
 }
@@ -589,6 +601,7 @@ int hsm_get_option(hsm_matcher *m, int key, int *value)
         case HSM_OPT_OUT_HI: *value = m->ohi; return HSM_OK;
         case HSM_OPT_STAGES: *value = m->stages; return HSM_OK;
         case HSM_OPT_LANE_CONFIG: *value = m->lane_config; return HSM_OK;
+        case HSM_OPT_FRAME_GROUPS: *value = m->frame_groups; return HSM_OK;
         default: return fail(HSM_ERR_ARG, "unknown option %d", key);
     }
 }
@@ -656,6 +669,21 @@ int hsm_iterate(hsm_matcher *m, int n_iter, int finalize)
     if (!m->pool.empty()) { ev = m->pool.back(); m->pool.pop_back(); }
     else { CUDA_TRY(cudaEventCreate(&ev.first)); CUDA_TRY(cudaEventCreate(&ev.second)); }
     CUDA_TRY(cudaEventRecord(ev.first, m->stream));
+    m->launch_frame0 = 0; m->launch_frames = m->frames; m->launch_stream = m->stream;
+    // Two frame groups on two streams (see matcher.hpp): frames are independent, so group B's CTAs fill
+    // the SMs that group A's last CTAs leave idle, and vice versa, for the whole loop.
+    const bool grouped = m->algorithm != 0 && m->algorithm != 3 && !p2p_active(m) &&
+                         m->frames >= 2 &&
+                         (m->frame_groups == 2 ||      // automatic: not for launches that are latency-bound anyway
+                          (m->frame_groups == 0 && (size_t)m->frames * m->H * m->W * m->Dp >= (size_t)500000));
+    if (grouped) {
+        if (!m->aux_stream) CUDA_TRY(cudaStreamCreateWithFlags(&m->aux_stream, cudaStreamNonBlocking));
+        if (!m->fork_event) CUDA_TRY(cudaEventCreateWithFlags(&m->fork_event, cudaEventDisableTiming));
+        if (!m->join_event) CUDA_TRY(cudaEventCreateWithFlags(&m->join_event, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventRecord(m->fork_event, m->stream));
+        CUDA_TRY(cudaStreamWaitEvent(m->aux_stream, m->fork_event, 0));
+    }
+    const int n_groups = grouped ? 2 : 1;
     for (int it = 0; it < n_iter; ++it) {
         if (m->algorithm == 0) {
             HSM_TRY(launch_directional(m));
@@ -663,6 +691,15 @@ int hsm_iterate(hsm_matcher *m, int n_iter, int finalize)
         }
         const int left = n_iter - it;
         const bool p2p = p2p_active(m);
+        const int cur_before = m->cur;
+      for (int group = 0; group < n_groups; ++group) {
+        if (grouped) {
+            const int half = (m->frames + 1) / 2;
+            m->launch_frame0 = group == 0 ? 0 : half;
+            m->launch_frames = group == 0 ? half : m->frames - half;
+            m->launch_stream = group == 0 ? m->stream : m->aux_stream;
+            m->cur = cur_before;                 // both groups read the same generation of the planes
+        }
         if (p2p) HSM_TRY(p2p_before_iteration(m));
         struct AfterIteration {          // tell the neighbours when this iteration's launch has been queued
             hsm_matcher *m; bool on;
@@ -689,6 +726,12 @@ int hsm_iterate(hsm_matcher *m, int n_iter, int finalize)
             HSM_TRY(p2p ? launch_tma_push_any(m, store_s) : launch_tma_any(m, store_s));
         else
             HSM_TRY(launch_fused_any(m, store_s));
+      }
+    }
+    m->launch_frame0 = 0; m->launch_frames = m->frames; m->launch_stream = m->stream;
+    if (grouped) {
+        CUDA_TRY(cudaEventRecord(m->join_event, m->aux_stream));
+        CUDA_TRY(cudaStreamWaitEvent(m->stream, m->join_event, 0));
     }
     CUDA_TRY(cudaEventRecord(ev.second, m->stream));
     m->pending.push_back(ev);

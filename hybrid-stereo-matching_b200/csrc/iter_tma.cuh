@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(NT, (NT == 256 && VPL == 1) ? HSM_TMA_MIN_BLOC
     const bool in_x = (x >= 0 && x < g.W);
     const int yb0 = a.olo + (int)blockIdx.y * a.band_rows;
     const int yb1 = min(yb0 + a.band_rows - 1, a.ohi);
-    const int frame = (int)blockIdx.z;
+    const int frame = a.frame0 + (int)blockIdx.z;
     const size_t fplane = (size_t)frame * g.plane_stride;
     const unsigned row_stride = (unsigned)g.W * (unsigned)g.Dp;
     const int n_rows = yb1 - yb0 + 3;                                    // rows yb0-1 .. yb1+1

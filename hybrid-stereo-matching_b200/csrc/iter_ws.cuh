@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(NT + 32, (NT == 256 && VPL == 1) ? HSM_WS_MIN_
     const int shift_l = (xs0 - 1) & 3, shift_r = (xs0 - SL::DCOV) & 3;
     const int yb0 = a.olo + (int)blockIdx.y * a.band_rows;
     const int yb1 = min(yb0 + a.band_rows - 1, a.ohi);
-    const int frame = (int)blockIdx.z;
+    const int frame = a.frame0 + (int)blockIdx.z;
     const int n_rows = yb1 - yb0 + 3;                                    // rows yb0-1 .. yb1+1
 
     if (tid == 0) {

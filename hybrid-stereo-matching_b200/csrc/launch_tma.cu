@@ -19,9 +19,9 @@ int launch_tma(hsm_matcher *m, bool store_s)
     const Geo g = geometry(m);
     constexpr int PX = NT / LPP, TX = PX - 2, SLOTS = NT + 2 * LPP;
     const int strips = (m->W + TX - 1) / TX;
-    IterArgs a = iter_args(m, strips, store_s);
+    IterArgs a = iter_args(m, strips, store_s, ((NT == 256) ? (VPL == 1 ? 3 : 2) : (VPL == 1 ? 2 : 1)));
     const int bands = (m->ohi - m->olo + 1 + a.band_rows - 1) / a.band_rows;
-    dim3 grid(strips, bands, m->frames);
+    dim3 grid(strips, bands, m->launch_frames);
     const bool dt_load = (m->data_term == 0);
     const bool full = (m->D == 4 * LPP * VPL);
     (void)PX;
@@ -41,7 +41,7 @@ int launch_tma(hsm_matcher *m, bool store_s)
     do {                                                                                                     \
         auto kernel = k_iter_tma<LPP, VPL, NT, T, F, HSM_PUSH>;                                                        \
         CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
-        kernel<<<grid, NT, smem, m->stream>>>(tw, tn, te, td, m->tmI.L, m->tmI.R, m->tmI.P, g, a, stages);                         \
+        kernel<<<grid, NT, smem, m->launch_stream>>>(tw, tn, te, td, m->tmI.L, m->tmI.R, m->tmI.P, g, a, stages);                         \
     } while (0)
     if (full) { if (dt_load) HSM_LAUNCH_TMA(true, true); else HSM_LAUNCH_TMA(false, true); }
     else { if (dt_load) HSM_LAUNCH_TMA(true, false); else HSM_LAUNCH_TMA(false, false); }

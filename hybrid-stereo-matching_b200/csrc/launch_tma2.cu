@@ -21,16 +21,16 @@ int launch_tma2(hsm_matcher *m, bool store_s, bool *launched)
     HSM_TRY(ensure_maps(m));
     const Geo g = geometry(m);
     const int strips = (m->W + TX - 1) / TX;
-    IterArgs a = iter_args(m, strips, store_s);
+    IterArgs a = iter_args(m, strips, store_s, ((NT == 256) ? (VPL == 1 ? 3 : 2) : (VPL == 1 ? 2 : 1)));
     const int bands = (m->ohi - m->olo + 1 + a.band_rows - 1) / a.band_rows;
-    dim3 grid(strips, bands, m->frames);
+    dim3 grid(strips, bands, m->launch_frames);
     const bool full = (m->D == 4 * LPP * VPL);
     const CUtensorMap &tw = m->tmW[m->cur], &tn = m->tmN[m->cur], &te = m->tmE[m->cur];
 #define HSM_LAUNCH_TMA2(F)                                                                                   \
     do {                                                                                                     \
         auto kernel = k_iter2_tma<LPP, VPL, NT, F>;                                                          \
         CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
-        kernel<<<grid, NT, smem, m->stream>>>(tw, tn, te, m->tmI.L, m->tmI.R, m->tmI.P, g, a, stages);       \
+        kernel<<<grid, NT, smem, m->launch_stream>>>(tw, tn, te, m->tmI.L, m->tmI.R, m->tmI.P, g, a, stages);       \
     } while (0)
     if (full) HSM_LAUNCH_TMA2(true); else HSM_LAUNCH_TMA2(false);
 #undef HSM_LAUNCH_TMA2

@@ -33,16 +33,16 @@ int launch_tmast(hsm_matcher *m, bool store_s, bool *launched)
     HSM_TRY(ensure_maps(m));
     const Geo g = geometry(m);
     const int strips = (m->W + TX - 1) / TX;
-    IterArgs a = iter_args(m, strips, store_s);
+    IterArgs a = iter_args(m, strips, store_s, ((NT == 256) ? (VPL == 1 ? 3 : 2) : (VPL == 1 ? 2 : 1)));
     const int bands = (m->ohi - m->olo + 1 + a.band_rows - 1) / a.band_rows;
-    dim3 grid(strips, bands, m->frames);
+    dim3 grid(strips, bands, m->launch_frames);
     const bool full = (m->D == 4 * LPP * VPL);
     const int in = m->cur, out = m->cur ^ 1;
 #define HSM_LAUNCH_TMAST(T, F)                                                                               \
     do {                                                                                                     \
         auto kernel = k_iter_tmast<LPP, VPL, NT, T, F, HSM_PUSH>;                                                      \
         CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
-        kernel<<<grid, NT, smem, m->stream>>>(m->tmW[in], m->tmN[in], m->tmE[in], m->tmD, m->tmI.L, m->tmI.R, \
+        kernel<<<grid, NT, smem, m->launch_stream>>>(m->tmW[in], m->tmN[in], m->tmE[in], m->tmD, m->tmI.L, m->tmI.R, \
                                               m->tmI.P, m->tsW[out], m->tsN[out], m->tsE[out], g, a, stages);  \
     } while (0)
     if (full) { if (dt_load) HSM_LAUNCH_TMAST(true, true); else HSM_LAUNCH_TMAST(false, true); }

@@ -13,9 +13,9 @@ int launch_ws(hsm_matcher *m, bool store_s)
     const Geo g = geometry(m);
     constexpr int PX = NT / LPP, TX = PX - 2, NW = NT / 32, XR = 4;
     const int strips = (m->W + TX - 1) / TX;
-    IterArgs a = iter_args(m, strips, store_s);
+    IterArgs a = iter_args(m, strips, store_s, ((NT == 256) ? (VPL == 1 ? 3 : 2) : (VPL == 1 ? 2 : 1)));
     const int bands = (m->ohi - m->olo + 1 + a.band_rows - 1) / a.band_rows;
-    dim3 grid(strips, bands, m->frames);
+    dim3 grid(strips, bands, m->launch_frames);
     const bool dt_load = (m->data_term == 0);
     const bool full = (m->D == 4 * LPP * VPL);
     const size_t stage_bytes = StageLayout<LPP, VPL, NT>::stage_bytes(m->Dp, dt_load);
@@ -33,7 +33,7 @@ int launch_ws(hsm_matcher *m, bool store_s)
     do {                                                                                                     \
         auto kernel = k_iter_ws<LPP, VPL, NT, T, F>;                                                         \
         CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
-        kernel<<<grid, NT + 32, smem, m->stream>>>(tw, tn, te, td, m->tmI.L, m->tmI.R, m->tmI.P, g, a, stages); \
+        kernel<<<grid, NT + 32, smem, m->launch_stream>>>(tw, tn, te, td, m->tmI.L, m->tmI.R, m->tmI.P, g, a, stages); \
     } while (0)
     if (full) { if (dt_load) HSM_LAUNCH_WS(true, true); else HSM_LAUNCH_WS(false, true); }
     else { if (dt_load) HSM_LAUNCH_WS(true, false); else HSM_LAUNCH_WS(false, false); }

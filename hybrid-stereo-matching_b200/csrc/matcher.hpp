@@ -104,7 +104,14 @@ struct hsm_matcher {
         unsigned ghost_off = 0;                  // element offset of the neighbour's ghost row inside its planes
     } peer[2];
     unsigned *mailbox = nullptr;                 // [0] written by the band above, [1] by the band below
-    unsigned p2p_iterations = 0;                 // iterations completed since hsm_peer_reset
+    unsigned p2p_iterations = 0;
+    // Frame groups: an iteration over >= 2 frames is launched as two kernels (first / second half of the
+    // frames) on two streams, so that one group's tail (SMs idling while the last CTAs finish) is filled by
+    // the other group's CTAs.  Set per launch by hsm_iterate; read by the launch_* functions.
+    int frame_groups = 0;                        // HSM_OPT_FRAME_GROUPS: 0 = automatic, 1 = one launch per iteration
+    int launch_frame0 = 0, launch_frames = 0;
+    cudaStream_t launch_stream = nullptr, aux_stream = nullptr;
+    cudaEvent_t fork_event = nullptr, join_event = nullptr;                 // iterations completed since hsm_peer_reset
     // statistics
     hsm_stats stats{};
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending, pool;
@@ -115,11 +122,11 @@ namespace hsm {
 
 // shared host helpers (defined in hsm_api.cu)
 Geo geometry(const hsm_matcher *m);
-int choose_band_rows(const hsm_matcher *m, int strips);
+int choose_band_rows(const hsm_matcher *m, int strips, int ctas_per_sm);
 int check_launch(hsm_matcher *m, const char *what);
 int ensure_maps(hsm_matcher *m);
 bool tma_supported(const hsm_matcher *m);
-IterArgs iter_args(hsm_matcher *m, int strips, bool store_s);   // everything but the tensor maps
+IterArgs iter_args(hsm_matcher *m, int strips, bool store_s, int ctas_per_sm);   // everything but the tensor maps
 
 // one BP iteration (or two, for algorithm 3) with the given kernel family; each lives in its own
 // translation unit.  `*launched` = false when the configuration cannot use that kernel.

@@ -25,8 +25,8 @@ class NumpyBandEngine(object):
                               None if prior is None else prior[rows], prior_trust_factor,
                               prior_influence_mode, reinit_messages=True)
 
-    def iterate(self, finalize):
-        mrf_numpy.iterate(self.state, 1)
+    def iterate(self, finalize, n_iter=1):
+        mrf_numpy.iterate(self.state, int(n_iter))
 
     def new_halo(self):
         return torch.empty(3 * self.n_cols * self.n_levels, dtype=torch.float32)

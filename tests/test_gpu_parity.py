@@ -121,6 +121,33 @@ def test_batch_equals_single_frames(hsm):
         assert np.array_equal(batched.message_field(4)[name], plane), name
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("algorithm", [5, 4, 2, 1])
+def test_frame_groups_do_not_change_results(hsm, algorithm):
+    """Two concurrent frame groups (HSM_OPT_FRAME_GROUPS = 2, the default for real workloads) == one
+    launch per iteration == single frames, for odd and even frame counts."""
+    from importlib import import_module
+    capi = import_module("hybrid-stereo-matching_b200._capi")
+    synth = import_module("hybrid-stereo-matching_b200.synth")
+    lefts, rights, priors = synth.synthetic_sequence(5, 30, 44, 20, base_seed=11)
+    single = hsm.StereoMRF((30, 44), 20)
+    single.set_option(capi.OPT_ALGORITHM, algorithm)
+    want = np.stack([single.lbp(lefts[i], rights[i], priors[i], prior_trust_factor=0.7,
+                                prior_influence_mode="const", n_iter=7) for i in range(5)])
+    for groups in (1, 2):
+        for count in (2, 5):
+            batched = hsm.StereoMRF((30, 44), 20, capacity=count)
+            batched.set_option(capi.OPT_ALGORITHM, algorithm)
+            batched.set_option(capi.OPT_FRAME_GROUPS, groups)
+            got = batched.lbp_batch(lefts[:count], rights[:count], priors[:count], prior_trust_factor=0.7,
+                                    prior_influence_mode="const", n_iter=7)
+            assert np.array_equal(got, want[:count]), (groups, count)
+            single.lbp(lefts[count - 1], rights[count - 1], priors[count - 1], prior_trust_factor=0.7,
+                       prior_influence_mode="const", n_iter=7)
+            for name, plane in single._message_field.items():
+                assert np.array_equal(batched.message_field(count - 1)[name], plane), (groups, count, name)
+
+
 def test_iteration_by_iteration_equals_one_call(hsm):
     """_update_message_fields() n times == loop_belief(n_iter=n) (mrf.py:130-133)."""
     case = C.SMALL_CASES[0]

@@ -43,10 +43,13 @@ if exchange == "p2p" and world > 1:
     dist.barrier()
     t2 = time.perf_counter()
 with engine.stream_context():
-    for it in range(n_iter):
-        engine.iterate(finalize=(it == n_iter - 1))
-        if exchange != "p2p" and it < n_iter - 1 and world > 1:
-            matcher._exchange()
+    if exchange == "p2p" or world == 1:
+        engine.iterate(finalize=True, n_iter=n_iter)
+    else:
+        for it in range(n_iter):
+            engine.iterate(finalize=(it == n_iter - 1))
+            if it < n_iter - 1:
+                matcher._exchange()
 torch.cuda.synchronize()
 if world > 1:
     dist.barrier()

@@ -16,7 +16,7 @@ for r in data:
     agg.setdefault(r[ki].split("(")[0], []).append(float(r[vi].replace(",", "")))
 total = sum(sum(v) for v in agg.values())
 lines = ["# ncu launch list of `python bench.py --steps 2 --warmup 3 --cpu-frames 0 --frames-per-step 128`",
-         "# (ncu --metrics gpu__time_duration.sum --clock-control none -c 500; serialised, cold cache: compare SHARES)",
+         "# (ncu --metrics gpu__time_duration.sum --clock-control none -c 700; serialised, cold cache: compare SHARES)",
          "%-60s %6s %12s %8s %10s" % ("kernel", "n", "total_us", "share", "avg_us")]
 for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
     lines.append("%-60s %6d %12.1f %7.2f%% %10.1f" % (k[:60], len(v), sum(v) / 1e3, 100 * sum(v) / total, sum(v) / len(v) / 1e3))
@@ -38,7 +38,7 @@ want = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__
         "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "launch__waves_per_multiprocessor",
         "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem", "smsp__inst_executed.sum",
         "lts__t_sector_hit_rate.pct", "gpc__cycles_elapsed.avg.per_second", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"]
-summary = ["# ncu --set full --clock-control none -k regex:k_iter_tma -s 60 -c 2 (same bench command; matches k_iter_tmast)"]
+summary = ["# ncu --set full --clock-control none -k regex:k_iter_tma -s 120 -c 2 (same bench command; matches k_iter_tmast)"]
 vals = {}
 for wname in want:
     for i, hh in enumerate(hdr):
@@ -57,7 +57,10 @@ def gb(s):
 i_r, i_w = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
 scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
 per = [float(r[i_r]) * scale[units[i_r]] + float(r[i_w]) * scale[units[i_w]] for r in dd]
-json.dump({"dram_bytes_per_launch": sum(per) / len(per), "frames_per_launch": 128,
+gi = hdr.index("launch__grid_size")
+frames_per_launch = 64       # bench.py --frames-per-step 128: one 128-frame chunk = two 64-frame groups
+json.dump({"dram_bytes_per_launch": sum(per) / len(per), "frames_per_launch": frames_per_launch,
+           "grid_size": dd[0][gi],
            "source": "profiles/%s_k_iter_tma_ncu_full.txt (dram__bytes_read.sum + dram__bytes_write.sum, mean of %d launches)" % (tag, len(per))},
           open(os.path.join(out_dir, "roofline_traffic.json"), "w"), indent=1)
 print(open(os.path.join(out_dir, "roofline_traffic.json")).read())
