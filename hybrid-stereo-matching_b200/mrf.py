@@ -239,8 +239,15 @@ class StereoMRF(object):
             out = np.empty((n_total, self._rows, self._cols), dtype=np.int64)
         assert out.shape == (n_total, self._rows, self._cols) and out.dtype == np.int64 \
             and out.flags["C_CONTIGUOUS"]
-        chunks = [(start, min(start + self.capacity, n_total)) for start in range(0, n_total, self.capacity)]
-        workers = self._lanes(max(1, min(int(lanes), len(chunks))))
+        # Chunk size: the capacity, but at least two chunks per lane when there is more than one capacity's
+        # worth of frames -- the first chunk's upload and the last chunk's download are the only transfers
+        # that cannot overlap compute, so they should be a small part of the call.
+        lanes = max(1, int(lanes))
+        chunk = self.capacity
+        if n_total > self.capacity and lanes > 1:
+            chunk = min(self.capacity, max(-(-n_total // (2 * lanes)), 8))
+        chunks = [(start, min(start + chunk, n_total)) for start in range(0, n_total, chunk)]
+        workers = self._lanes(max(1, min(lanes, len(chunks))))
         for index, (start, stop) in enumerate(chunks):
             lane = workers[index % len(workers)]
             lane.synchronize()
