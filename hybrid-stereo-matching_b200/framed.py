@@ -28,6 +28,18 @@ def select_priors(prior_info, frame_timestamps):
     return np.asarray(prior_info["priors"])
 
 
+def next_n_iter(n_iter, last_duration_ms, frame_budget_ms, min_iter=1, max_iter=10, adaptive=True):
+    """Iteration budget of the online loop (online_processing.py:122-127): when the previous frame used
+    less than 80 % of its time budget grow by 20 % + 1, otherwise halve; clamp to [min_iter, max_iter].
+    ``frame_budget_ms`` = nominal frame length x SNN slow-down factor.  With ``adaptive=False`` the
+    reference always runs ``max_iter`` iterations."""
+    if not adaptive:
+        return max_iter
+    used = last_duration_ms / frame_budget_ms
+    n_iter = int(n_iter + 0.2 * n_iter + 1 if used < 0.8 else n_iter - 0.5 * n_iter)
+    return min(max_iter, max(min_iter, n_iter))
+
+
 class FramebasedStereoMatching(object):
     def __init__(self, resolution, max_disparity, algorithm="mrf", inputs=None, capacity=64, device=0,
                  matcher_factory=None):

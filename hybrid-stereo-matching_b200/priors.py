@@ -78,3 +78,24 @@ def normalise_contrast(images, device=0):
     _capi.check(_capi.lib().hsm_normalise_contrast(stack.shape[0], stack.shape[1], stack.shape[2], ptr(stack),
                                                    ptr(out), int(device)))
     return out[0] if single else out
+
+
+def prepare_frames(images, crop_region=None, resolution=None, scale_down_factor=(1, 1), adjust_contrast=False,
+                   device=0):
+    """The array part of ``load_frames`` (frames_io.py:91-131): crop every frame to ``resolution`` =
+    (width, height) at ``crop_region`` = (column, row) of the top-left corner, then (optionally) stretch each
+    frame's contrast to [0, 1] on the GPU.  Down-scaling (``skimage.transform.rescale``, frames_io.py:99-101)
+    is an un-vendored third-party resampler whose output cannot be pinned here, so any
+    factor other than (1, 1) is refused rather than approximated."""
+    if tuple(int(f) for f in scale_down_factor) != (1, 1):
+        raise NotImplementedError("scale_down_factor != (1, 1): skimage.rescale semantics are not reproduced")
+    images = np.asarray(images)
+    if images.ndim == 2:
+        images = images[None]
+    if crop_region is not None and resolution is not None:
+        col_start, row_start = crop_region                      # frames_io.py:91-95: x, y order
+        dx, dy = resolution
+        images = images[:, row_start:row_start + dy, col_start:col_start + dx]
+    if adjust_contrast:
+        return normalise_contrast(images, device=device)
+    return np.ascontiguousarray(images)

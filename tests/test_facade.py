@@ -95,3 +95,18 @@ def test_facade_batched_cuda_equals_sequential_reference(hsm):
     got = online.run_one_frame(lefts[0], rights[0], prior32, n_iter=4)
     want = mrf_numpy.OracleMRF((14, 20), levels).lbp(lefts[0], rights[0], prior32, n_iter=4)
     assert np.array_equal(got, want) and got.dtype == np.int64
+
+
+def test_online_iteration_budget_rule():
+    """next_n_iter == the expression in online_processing.py:122-127, over a sweep of states."""
+    from importlib import import_module
+    framed = import_module("hybrid-stereo-matching_b200.framed")
+    for min_iter, max_iter in ((1, 10), (2, 50), (5, 5)):
+        for n_iter in range(0, 60, 3):
+            for duration in (0.0, 10.0, 39.9, 40.0, 41.0, 200.0):
+                for budget in (50.0, 50.0 * 2.5):
+                    t = duration / budget
+                    want = int(n_iter + 0.2 * n_iter + 1 if t < 0.8 else n_iter - 0.5 * n_iter)
+                    want = min(max_iter, max(min_iter, want))
+                    assert framed.next_n_iter(n_iter, duration, budget, min_iter, max_iter) == want
+    assert framed.next_n_iter(3, 1.0, 50.0, 1, 10, adaptive=False) == 10

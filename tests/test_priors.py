@@ -95,3 +95,21 @@ def test_contrast_normalisation_bits(hsm):
         want = frames_numpy.normalise_contrast(frames[i])
         assert got[i].tobytes() == want.tobytes(), i
     assert priors.normalise_contrast(frames[0]).tobytes() == frames_numpy.normalise_contrast(frames[0]).tobytes()
+
+
+@pytest.mark.gpu
+def test_prepare_frames_crop_and_contrast(hsm):
+    """crop (x, y order) + per-frame contrast stretch == frames_io.py:91-95, 103-109, 130-131."""
+    from importlib import import_module
+    priors = import_module("hybrid-stereo-matching_b200.priors")
+    rng = np.random.default_rng(5)
+    frames = np.round(rng.random((3, 60, 80)) * 255.0)
+    got = priors.prepare_frames(frames, crop_region=(11, 7), resolution=(40, 30), adjust_contrast=True)
+    assert got.shape == (3, 30, 40)
+    for i in range(3):
+        want = frames_numpy.normalise_contrast(frames[i][7:37, 11:51])
+        assert got[i].tobytes() == want.tobytes(), i
+    plain = priors.prepare_frames(frames, crop_region=(11, 7), resolution=(40, 30))
+    assert np.array_equal(plain, frames[:, 7:37, 11:51])
+    with pytest.raises(NotImplementedError):
+        priors.prepare_frames(frames, scale_down_factor=(2, 2))
