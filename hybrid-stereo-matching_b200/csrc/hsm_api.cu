@@ -684,6 +684,11 @@ int hsm_iterate(hsm_matcher *m, int n_iter, int finalize)
         CUDA_TRY(cudaStreamWaitEvent(m->aux_stream, m->fork_event, 0));
     }
     const int n_groups = grouped ? 2 : 1;
+    // one kernel per iteration: let the next iteration's CTAs set up while this one drains (with frame
+    // groups the other group's CTAs are the better use of those SMs; the peer-to-peer flags sit between
+    // the kernels of a stream, so nothing is adjacent there)
+    static const bool pdl_enabled = getenv("HSM_NO_PDL") == nullptr;
+    m->launch_pdl = pdl_enabled && !grouped && !p2p_active(m);
     for (int it = 0; it < n_iter; ++it) {
         if (m->algorithm == 0) {
             HSM_TRY(launch_directional(m));

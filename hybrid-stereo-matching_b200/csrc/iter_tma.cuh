@@ -72,6 +72,13 @@ __device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *map, u
         : "memory");
 }
 
+// Programmatic dependent launch: when the launch carries the programmatic-stream-serialization
+// attribute, the CTAs of iteration k+1 may become resident while iteration k drains and run their
+// prologue (barrier init, shared-memory setup); pdl_wait() blocks until iteration k has completed and
+// its stores are visible.  Without the attribute both are no-ops.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 #ifndef HSM_TMA_MIN_BLOCKS
 #define HSM_TMA_MIN_BLOCKS 3
 #endif
@@ -176,6 +183,8 @@ __global__ void __launch_bounds__(NT, (NT == 256 && VPL == 1) ? HSM_TMA_MIN_BLOC
             if (a.has_prior) tma_load_3d(img + SL::L_BYTES + SL::R_BYTES, &tmP, &full[s], xs0 - 1 - shift_l, yy, frame);
         }
     };
+    pdl_launch_dependents();
+    pdl_wait();                                 // everything above overlaps the previous iteration's tail
     if (tid == 0) {
         const int first = n_rows < stages ? n_rows : stages;
         for (int s = 0; s < first; ++s) issue(s, s);

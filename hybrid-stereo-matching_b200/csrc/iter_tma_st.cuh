@@ -102,6 +102,8 @@ __global__ void __launch_bounds__(NT, (NT == 256 && VPL == 1) ? HSM_TMA_MIN_BLOC
             if (a.has_prior) tma_load_3d(img + SL::L_BYTES + SL::R_BYTES, &tmP, &full[s], xs0 - 1 - shift_l, yy, frame);
         }
     };
+    pdl_launch_dependents();
+    pdl_wait();                                 // everything above overlaps the previous iteration's tail
     if (tid == 0) {
         const int first = n_rows < stages ? n_rows : stages;
         for (int s = 0; s < first; ++s) issue(s, s);

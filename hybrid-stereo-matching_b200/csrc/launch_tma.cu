@@ -37,11 +37,13 @@ int launch_tma(hsm_matcher *m, bool store_s)
     const size_t smem = fixed_bytes + (size_t)stages * stage_bytes;
     if (smem > (size_t)227 * 1024) return fail(HSM_ERR_ARG, "fused TMA kernel needs %zu bytes of shared memory", smem);
     const CUtensorMap &tw = m->tmW[m->cur], &tn = m->tmN[m->cur], &te = m->tmE[m->cur], &td = m->tmD;
+    cudaLaunchAttribute pdl_attr;
+    cudaLaunchConfig_t cfg = launch_config(m, grid, NT, smem, &pdl_attr);
 #define HSM_LAUNCH_TMA(T, F)                                                                                 \
     do {                                                                                                     \
         auto kernel = k_iter_tma<LPP, VPL, NT, T, F, HSM_PUSH>;                                                        \
         CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
-        kernel<<<grid, NT, smem, m->launch_stream>>>(tw, tn, te, td, m->tmI.L, m->tmI.R, m->tmI.P, g, a, stages);                         \
+        CUDA_TRY(cudaLaunchKernelEx(&cfg, kernel, tw, tn, te, td, m->tmI.L, m->tmI.R, m->tmI.P, g, a, stages));   \
     } while (0)
     if (full) { if (dt_load) HSM_LAUNCH_TMA(true, true); else HSM_LAUNCH_TMA(false, true); }
     else { if (dt_load) HSM_LAUNCH_TMA(true, false); else HSM_LAUNCH_TMA(false, false); }

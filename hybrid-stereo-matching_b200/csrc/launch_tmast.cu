@@ -38,12 +38,14 @@ int launch_tmast(hsm_matcher *m, bool store_s, bool *launched)
     dim3 grid(strips, bands, m->launch_frames);
     const bool full = (m->D == 4 * LPP * VPL);
     const int in = m->cur, out = m->cur ^ 1;
+    cudaLaunchAttribute pdl_attr;
+    cudaLaunchConfig_t cfg = launch_config(m, grid, NT, smem, &pdl_attr);
 #define HSM_LAUNCH_TMAST(T, F)                                                                               \
     do {                                                                                                     \
         auto kernel = k_iter_tmast<LPP, VPL, NT, T, F, HSM_PUSH>;                                                      \
         CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
-        kernel<<<grid, NT, smem, m->launch_stream>>>(m->tmW[in], m->tmN[in], m->tmE[in], m->tmD, m->tmI.L, m->tmI.R, \
-                                              m->tmI.P, m->tsW[out], m->tsN[out], m->tsE[out], g, a, stages);  \
+        CUDA_TRY(cudaLaunchKernelEx(&cfg, kernel, m->tmW[in], m->tmN[in], m->tmE[in], m->tmD, m->tmI.L, m->tmI.R,   \
+                                    m->tmI.P, m->tsW[out], m->tsN[out], m->tsE[out], g, a, stages));           \
     } while (0)
     if (full) { if (dt_load) HSM_LAUNCH_TMAST(true, true); else HSM_LAUNCH_TMAST(false, true); }
     else { if (dt_load) HSM_LAUNCH_TMAST(true, false); else HSM_LAUNCH_TMAST(false, false); }

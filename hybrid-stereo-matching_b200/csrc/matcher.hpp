@@ -14,6 +14,7 @@
 
 #include <algorithm>
 #include <cstdarg>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -111,6 +112,7 @@ struct hsm_matcher {
     int frame_groups = 0;                        // HSM_OPT_FRAME_GROUPS: 0 = automatic, 1 = one launch per iteration
     int launch_frame0 = 0, launch_frames = 0;
     cudaStream_t launch_stream = nullptr, aux_stream = nullptr;
+    bool launch_pdl = false;                     // programmatic dependent launch (one kernel per iteration only)
     cudaEvent_t fork_event = nullptr, join_event = nullptr;                 // iterations completed since hsm_peer_reset
     // statistics
     hsm_stats stats{};
@@ -122,6 +124,22 @@ namespace hsm {
 
 // shared host helpers (defined in hsm_api.cu)
 Geo geometry(const hsm_matcher *m);
+// Launch configuration of an iteration kernel on m->launch_stream; with m->launch_pdl the launch may
+// overlap its prologue with the previous kernel's tail (see pdl_wait in iter_tma.cuh).
+inline cudaLaunchConfig_t launch_config(const hsm_matcher *m, dim3 grid, int threads, size_t smem,
+                                        cudaLaunchAttribute *attr)
+{
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = m->launch_stream;
+    attr->id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr->val.programmaticStreamSerializationAllowed = m->launch_pdl ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cfg;
+}
 int choose_band_rows(const hsm_matcher *m, int strips, int ctas_per_sm);
 int check_launch(hsm_matcher *m, const char *what);
 int ensure_maps(hsm_matcher *m);
