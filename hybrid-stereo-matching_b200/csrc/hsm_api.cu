@@ -107,6 +107,7 @@ int ensure_ready(hsm_matcher *m)
         CUDA_TRY(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
         m->own_stream = true;
     }
+    CUDA_TRY(cudaDeviceGetAttribute(&m->sm_count, cudaDevAttrMultiProcessorCount, m->device));
     m->arena_bytes = arena_layout(m, false);
     CUDA_TRY(cudaMalloc(&m->arena, m->arena_bytes));
     arena_layout(m, true);
@@ -253,6 +254,22 @@ int choose_band_rows(const hsm_matcher *m, int strips, int ctas_per_sm)
     const long target = 148L * std::max(1, ctas_per_sm) * (grouped ? 4 : 6);
     long bands = std::max((target + per_band - 1) / per_band, (long)(rows + 63) / 64);
     bands = std::max(1L, std::min<long>(bands, std::max(1, rows / min_rows)));
+    return (int)((rows + bands - 1) / bands);
+}
+
+// Persistent dataflow kernel: there is no drain per iteration and no launch per iteration, so the only costs
+// of a band are its two halo rows against the parallelism it removes.  A tile of iteration k+1 needs its
+// neighbours of iteration k, handed out one iteration's worth of tiles earlier, so an iteration must be
+// several rounds of resident CTAs long or CTAs wait: aim at ~3.5 tiles per resident CTA per iteration,
+// bands of 4..64 rows.
+int choose_flow_band_rows(const hsm_matcher *m, int strips, int ctas_per_sm)
+{
+    const int rows = m->ohi - m->olo + 1;
+    if (m->band_rows > 0) return std::min(m->band_rows, rows);
+    const long per_band = (long)strips * m->frames;
+    const long target = 7L * m->sm_count * std::max(1, ctas_per_sm) / 2;
+    long bands = std::max((target + per_band - 1) / per_band, (long)(rows + 63) / 64);
+    bands = std::max(1L, std::min<long>(bands, std::max(1, rows / 4)));
     return (int)((rows + bands - 1) / bands);
 }
 }  // namespace hsm
@@ -523,6 +540,7 @@ int hsm_destroy(hsm_matcher *m)
         for (auto &pr : m->pending) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
         for (auto &pr : m->pool) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
         cudaFree(m->arena);
+        if (m->flow_state) cudaFree(m->flow_state);
         if (m->aux_stream) cudaStreamDestroy(m->aux_stream);
         if (m->fork_event) cudaEventDestroy(m->fork_event);
         if (m->join_event) cudaEventDestroy(m->join_event);
@@ -554,7 +572,7 @@ int hsm_set_option(hsm_matcher *m, int key, int value)
     if (!m) return fail(HSM_ERR_ARG, "null matcher");
     switch (key) {
         case HSM_OPT_ALGORITHM:
-            if (value < 0 || value > 5) return fail(HSM_ERR_ARG, "algorithm must be 0..5");
+            if (value < 0 || value > 6) return fail(HSM_ERR_ARG, "algorithm must be 0..6");
             m->algorithm = value; return HSM_OK;
         case HSM_OPT_BAND_ROWS:
             if (value < 0) return fail(HSM_ERR_ARG, "band_rows must be >= 0");
@@ -670,6 +688,22 @@ int hsm_iterate(hsm_matcher *m, int n_iter, int finalize)
     else { CUDA_TRY(cudaEventCreate(&ev.first)); CUDA_TRY(cudaEventCreate(&ev.second)); }
     CUDA_TRY(cudaEventRecord(ev.first, m->stream));
     m->launch_frame0 = 0; m->launch_frames = m->frames; m->launch_stream = m->stream;
+    // algorithm 6: the whole loop is one persistent launch (falls back to 5 when it does not apply)
+    // (also chosen automatically for one large frame: with nothing to overlap an iteration's drain with, the
+    // persistent kernel is 5-18 % faster from 640x480xD64 up; small frames are latency-bound and lose to it)
+    const bool flow_auto = m->algorithm == 5 && m->frames == 1 &&
+                           (size_t)m->H * m->W * m->Dp >= (size_t)8000000;
+    if ((m->algorithm == 6 || flow_auto) && tma_supported(m) && !p2p_active(m) && n_iter >= 2) {
+        bool launched = false;
+        HSM_TRY(launch_flow_any(m, n_iter, finalize != 0, &launched));
+        if (launched) {
+            CUDA_TRY(cudaEventRecord(ev.second, m->stream));
+            m->pending.push_back(ev);
+            m->stats.iterations += (uint64_t)n_iter;
+            m->s_valid = finalize != 0;
+            return HSM_OK;
+        }
+    }
     // Two frame groups on two streams (see matcher.hpp): frames are independent, so group B's CTAs fill
     // the SMs that group A's last CTAs leave idle, and vice versa, for the whole loop.
     const bool grouped = m->algorithm != 0 && m->algorithm != 3 && !p2p_active(m) &&
@@ -718,9 +752,9 @@ int hsm_iterate(hsm_matcher *m, int n_iter, int finalize)
             if (launched) { ++it; continue; }
         }
         const bool store_s = finalize && (it == n_iter - 1);
-        if (p2p && !(m->algorithm == 5 || m->algorithm == 2) )
+        if (p2p && !(m->algorithm == 5 || m->algorithm == 6 || m->algorithm == 2))
             return fail(HSM_ERR_STATE, "peer-to-peer halo push needs algorithm 2 or 5");
-        if (m->algorithm == 5 && tma_supported(m)) {
+        if ((m->algorithm == 5 || m->algorithm == 6) && tma_supported(m)) {
             bool launched = false;
             HSM_TRY(p2p ? launch_tmast_push_any(m, store_s, &launched) : launch_tmast_any(m, store_s, &launched));
             if (launched) continue;

@@ -18,22 +18,45 @@ __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_fence() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-template <int LPP, int VPL, int NT, bool DT_LOAD, bool FULL, bool PUSH>
-__global__ void __launch_bounds__(NT, (NT == 256 && VPL == 1) ? HSM_TMA_MIN_BLOCKS : 1)
-    k_iter_tmast(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmN,
-               const __grid_constant__ CUtensorMap tmE, const __grid_constant__ CUtensorMap tmD,
-               const __grid_constant__ CUtensorMap tmL, const __grid_constant__ CUtensorMap tmR,
-               const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUtensorMap tsW,
-               const __grid_constant__ CUtensorMap tsN, const __grid_constant__ CUtensorMap tsE, Geo g, IterArgs a,
-               int stages)
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned *p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu(unsigned *p, unsigned v)
+{
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// Dataflow kernel: publish a finished tile.  Called by the thread that issued the tile's bulk stores, once they
+// are no longer needed in flight: wait for their completion, then release the tile's progress counter.
+__device__ __forceinline__ void flow_publish(unsigned *flag, unsigned value)
+{
+    tma_store_wait_all();
+    asm volatile("fence.proxy.async;" ::: "memory");
+    __threadfence();
+    st_release_gpu(flag, value);
+}
+
+// One task of the fused iteration: strip `bx`, band `by` of frame `frame`.  Shared by the one-launch-per-
+// iteration kernel (k_iter_tmast: one task per CTA) and the persistent dataflow kernel (iter_flow.cuh: a CTA
+// runs task after task; FLOW = true).  `stage` / `phase` are the position in the ring of row stages; they carry
+// over from task to task (every load issued by a task is consumed by it, so the ring stays consistent).
+template <int LPP, int VPL, int NT, bool DT_LOAD, bool FULL, bool PUSH, bool FLOW>
+__device__ __forceinline__ void tmast_task(const CUtensorMap *tmW, const CUtensorMap *tmN, const CUtensorMap *tmE,
+                                           const CUtensorMap *tmD, const CUtensorMap *tmL, const CUtensorMap *tmR,
+                                           const CUtensorMap *tmP, const CUtensorMap *tsW, const CUtensorMap *tsN,
+                                           const CUtensorMap *tsE, const Geo &g, const IterArgs &a, const int stages,
+                                           const int bx, const int by, const int frame, const bool STORE_S,
+                                           unsigned char *smem_raw, int &stage, uint32_t &phase, const bool first_task,
+                                           unsigned *publish_flag = nullptr, unsigned publish_value = 0)
 {
     using SL = StageLayout<LPP, VPL, NT>;
-    const bool STORE_S = a.store_s != 0;
     constexpr int PX = NT / LPP;
     constexpr int TX = PX - 2;
     constexpr int SLOTS = NT + 2 * LPP;
     constexpr int NPL = DT_LOAD ? 4 : 3;
-    extern __shared__ __align__(1024) unsigned char smem_raw[];
 
     const int tid = threadIdx.x;
     const int px = tid / LPP;
@@ -48,16 +71,14 @@ __global__ void __launch_bounds__(NT, (NT == 256 && VPL == 1) ? HSM_TMA_MIN_BLOC
     unsigned char *ost = smem_raw + (size_t)stages * stage_bytes;
     float4 *exch = reinterpret_cast<float4 *>(ost + 6u * ost_bytes);
     uint64_t *full = reinterpret_cast<uint64_t *>(exch + 2 * VPL * SLOTS);
-    uint64_t *xbar = full + stages;                                      // W' exchange barrier (all NT threads)
     auto ex = [&](int par, int v, int slot) -> float4 & { return exch[(par * VPL + v) * SLOTS + slot]; };
 
-    const int xs0 = (int)blockIdx.x * TX;
+    const int xs0 = bx * TX;
     const int shift_l = (xs0 - 1) & 3, shift_r = (xs0 - SL::DCOV) & 3;    // see StageLayout
     const int x = xs0 - 1 + px;
     const bool in_x = (x >= 0 && x < g.W);
-    const int yb0 = a.olo + (int)blockIdx.y * a.band_rows;
+    const int yb0 = a.olo + by * a.band_rows;
     const int yb1 = min(yb0 + a.band_rows - 1, a.ohi);
-    const int frame = a.frame0 + (int)blockIdx.z;
     const size_t fplane = (size_t)frame * g.plane_stride;
     const unsigned row_stride = (unsigned)g.W * (unsigned)g.Dp;
     const int n_rows = yb1 - yb0 + 3;                                    // rows yb0-1 .. yb1+1
@@ -68,16 +89,17 @@ __global__ void __launch_bounds__(NT, (NT == 256 && VPL == 1) ? HSM_TMA_MIN_BLOC
     const bool st_s = in_x && px >= 1 && px <= PX - 2;         // S' goes out with plain stores (last iteration only)
     const int rd_slot = (x < 0) ? (NT + LPP + ln.c) : (tid + LPP);
 
-    if (tid == 0) {
-        for (int s = 0; s < stages; ++s) mbar_init(&full[s], 1);
-        mbar_init(xbar, NT);
-        mbar_fence_init();
-    }
-    if (tid < 2 * LPP) {
+    if (first_task) {
+        if (tid == 0) {
+            for (int s = 0; s < stages; ++s) mbar_init(&full[s], 1);
+            mbar_fence_init();
+        }
+        if (tid < 2 * LPP) {
 #pragma unroll
-        for (int v = 0; v < VPL; ++v) ex(0, v, NT + tid) = ex(1, v, NT + tid) = zero4();
+            for (int v = 0; v < VPL; ++v) ex(0, v, NT + tid) = ex(1, v, NT + tid) = zero4();
+        }
+        __syncthreads();
     }
-    __syncthreads();
 
     // producer side (thread 0): one bulk tensor copy per plane into stage s for row index r
     auto issue = [&](int r, int s) {
@@ -87,26 +109,35 @@ __global__ void __launch_bounds__(NT, (NT == 256 && VPL == 1) ? HSM_TMA_MIN_BLOC
         unsigned tx = NPL * row_floats * 4u;
         if (!DT_LOAD) tx += SL::LBOX * 4u + SL::NRB * SL::RBOX * 4u + (a.has_prior ? SL::LBOX * 4u : 0u);
         mbar_expect_tx(&full[s], tx);
-        tma_load_4d(dst, &tmW, &full[s], 0, xs0 - 1, yy, frame);
-        tma_load_4d(dst + row_floats, &tmN, &full[s], 0, xs0 - 1, yy, frame);
-        tma_load_4d(dst + 2 * row_floats, &tmE, &full[s], 0, xs0 - 1, yy, frame);
+        tma_load_4d(dst, tmW, &full[s], 0, xs0 - 1, yy, frame);
+        tma_load_4d(dst + row_floats, tmN, &full[s], 0, xs0 - 1, yy, frame);
+        tma_load_4d(dst + 2 * row_floats, tmE, &full[s], 0, xs0 - 1, yy, frame);
         if (DT_LOAD) {
-            tma_load_4d(dst + 3 * row_floats, &tmD, &full[s], 0, xs0 - 1, yy, frame);
+            tma_load_4d(dst + 3 * row_floats, tmD, &full[s], 0, xs0 - 1, yy, frame);
         } else {
             unsigned char *img = stage_ptr + planes_bytes;
-            tma_load_3d(img, &tmL, &full[s], xs0 - 1 - shift_l, yy, frame);
+            tma_load_3d(img, tmL, &full[s], xs0 - 1 - shift_l, yy, frame);
 #pragma unroll
             for (int b = 0; b < SL::NRB; ++b)
-                tma_load_3d(img + SL::L_BYTES + b * SL::RBOX * 4, &tmR, &full[s],
+                tma_load_3d(img + SL::L_BYTES + b * SL::RBOX * 4, tmR, &full[s],
                             xs0 - SL::DCOV - shift_r + b * SL::RBOX, yy, frame);
-            if (a.has_prior) tma_load_3d(img + SL::L_BYTES + SL::R_BYTES, &tmP, &full[s], xs0 - 1 - shift_l, yy, frame);
+            if (a.has_prior) tma_load_3d(img + SL::L_BYTES + SL::R_BYTES, tmP, &full[s], xs0 - 1 - shift_l, yy, frame);
         }
     };
-    pdl_launch_dependents();
-    pdl_wait();                                 // everything above overlaps the previous iteration's tail
+    if (!FLOW) {
+        pdl_launch_dependents();
+        pdl_wait();                             // everything above overlaps the previous iteration's tail
+    }
     if (tid == 0) {
         const int first = n_rows < stages ? n_rows : stages;
-        for (int s = 0; s < first; ++s) issue(s, s);
+        int s_at = stage;
+        for (int s = 0; s < first; ++s) {
+            issue(s, s_at);
+            if (++s_at == stages) s_at = 0;
+        }
+        // dataflow kernel: the previous tile of this CTA is published only now, so that the completion
+        // of its stores overlaps this tile's dependency wait and first loads
+        if (FLOW && publish_flag) flow_publish(publish_flag, publish_value);
     }
 
     float *Sout = a.Sout + fplane;
@@ -136,8 +167,6 @@ __global__ void __launch_bounds__(NT, (NT == 256 && VPL == 1) ? HSM_TMA_MIN_BLOC
     const unsigned plane_f4 = row_floats / 4;
     const float4 *lane_base = reinterpret_cast<const float4 *>(smem_raw) + lane_f4;
     const unsigned char *img_base = smem_raw + planes_bytes;
-    int stage = 0;
-    uint32_t phase = 0;
     // element offset of (row y, this lane's pixel and chunk) inside the frame; advanced by one row per step
     // (x may be -1 or W for halo lanes: the wrap-around cancels when the neighbour offset is added)
     unsigned row_off = (unsigned)yb0 * row_stride + (unsigned)x * (unsigned)g.Dp + 4u * (unsigned)ln.c;
@@ -251,8 +280,8 @@ __global__ void __launch_bounds__(NT, (NT == 256 && VPL == 1) ? HSM_TMA_MIN_BLOC
         __syncthreads();                       // the row's only CTA barrier: W' published, stage consumed
         refill(y - yb0 + 1);
         if (tid == 0) {
-            if (y <= yb1) tma_store_row(&tsW, 0, par, y);
-            if (y > yb0 + 1) { tma_store_row(&tsN, 1, par ^ 1, y - 2); tma_store_row(&tsE, 2, par ^ 1, y - 2); }
+            if (y <= yb1) tma_store_row(tsW, 0, par, y);
+            if (y > yb0 + 1) { tma_store_row(tsN, 1, par ^ 1, y - 2); tma_store_row(tsE, 2, par ^ 1, y - 2); }
             tma_store_commit();
         }
         // X = S'(y, x) + W'(y, x)
@@ -307,11 +336,29 @@ __global__ void __launch_bounds__(NT, (NT == 256 && VPL == 1) ? HSM_TMA_MIN_BLOC
     __syncthreads();
     if (tid == 0) {
         const int last_par = (yb1 + 1 - yb0) & 1;
-        tma_store_row(&tsN, 1, last_par, yb1);
-        tma_store_row(&tsE, 2, last_par, yb1);
+        tma_store_row(tsN, 1, last_par, yb1);
+        tma_store_row(tsE, 2, last_par, yb1);
         tma_store_commit();
-        tma_store_wait_read();
+        tma_store_wait_read();                  // (dataflow kernel: completion is awaited by flow_publish)
     }
+}
+
+template <int LPP, int VPL, int NT, bool DT_LOAD, bool FULL, bool PUSH>
+__global__ void __launch_bounds__(NT, (NT == 256 && VPL == 1) ? HSM_TMA_MIN_BLOCKS : 1)
+    k_iter_tmast(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmN,
+               const __grid_constant__ CUtensorMap tmE, const __grid_constant__ CUtensorMap tmD,
+               const __grid_constant__ CUtensorMap tmL, const __grid_constant__ CUtensorMap tmR,
+               const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUtensorMap tsW,
+               const __grid_constant__ CUtensorMap tsN, const __grid_constant__ CUtensorMap tsE, Geo g, IterArgs a,
+               int stages)
+{
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    int stage = 0;
+    uint32_t phase = 0;
+    tmast_task<LPP, VPL, NT, DT_LOAD, FULL, PUSH, false>(&tmW, &tmN, &tmE, &tmD, &tmL, &tmR, &tmP, &tsW, &tsN, &tsE, g,
+                                                         a, stages, (int)blockIdx.x, (int)blockIdx.y,
+                                                         a.frame0 + (int)blockIdx.z, a.store_s != 0, smem_raw, stage,
+                                                         phase, true);
 }
 
 }  // namespace hsm

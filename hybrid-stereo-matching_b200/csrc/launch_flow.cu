@@ -1,0 +1,89 @@
+// Launch code of the persistent dataflow kernel (see iter_flow.cuh, matcher.hpp).
+#include "matcher.hpp"
+#include "iter_flow.cuh"
+
+namespace hsm {
+
+namespace {
+
+template <int LPP, int VPL, int NT>
+int launch_flow(hsm_matcher *m, int n_iter, bool finalize, bool *launched)
+{
+    *launched = false;
+    constexpr int PX = NT / LPP, TX = PX - 2, SLOTS = NT + 2 * LPP;
+    const bool dt_load = (m->data_term == 0);
+    const size_t stage_bytes = StageLayout<LPP, VPL, NT>::stage_bytes(m->Dp, dt_load);
+    const size_t ost_bytes = ((size_t)TX * m->Dp * 4 + 127) & ~(size_t)127;
+    const size_t fixed_bytes = 6 * ost_bytes + (size_t)2 * VPL * SLOTS * 16 + 128;
+    const int target_ctas = (NT == 256) ? (VPL == 1 ? 3 : 2) : (VPL == 1 ? 2 : 1);
+    int stages = m->stages;
+    if (stages <= 0) {
+        const size_t budget = (size_t)227 * 1024 / target_ctas - 1024;
+        stages = 3;
+        while (stages > 2 && fixed_bytes + stages * stage_bytes > budget) --stages;
+    }
+    const size_t smem = fixed_bytes + (size_t)stages * stage_bytes;
+    if (smem > (size_t)227 * 1024) return HSM_OK;
+    HSM_TRY(ensure_maps(m));
+    const Geo g = geometry(m);
+    const int strips = (m->W + TX - 1) / TX;
+    m->launch_frame0 = 0; m->launch_frames = m->frames; m->launch_stream = m->stream;
+    IterArgs a = iter_args(m, strips, false, target_ctas);
+    a.band_rows = choose_flow_band_rows(m, strips, target_ctas);
+    const int rows = m->ohi - m->olo + 1;
+    const int bands = (rows + a.band_rows - 1) / a.band_rows;
+    const size_t tiles = (size_t)m->frames * bands * strips;
+    if (tiles * (size_t)n_iter >= 0x7fffffffull) return HSM_OK;
+    // counter + per-tile progress, zeroed for every launch
+    const size_t need = (tiles + 1) * sizeof(unsigned);
+    if (m->flow_bytes < need) {
+        if (m->flow_state) CUDA_TRY(cudaFree(m->flow_state));
+        m->flow_state = nullptr; m->flow_bytes = 0;
+        CUDA_TRY(cudaMalloc(&m->flow_state, need));
+        m->flow_bytes = need;
+    }
+    CUDA_TRY(cudaMemsetAsync(m->flow_state, 0, need, m->stream));
+    FlowArgs f;
+    f.counter = m->flow_state; f.done = m->flow_state + 1;
+    f.n_iter = n_iter; f.frames = m->frames; f.bands = bands; f.strips = strips;
+    f.cur = m->cur; f.finalize = finalize ? 1 : 0;
+    FlowMaps maps;
+    for (int i = 0; i < 2; ++i) {
+        maps.tmW[i] = m->tmW[i]; maps.tmN[i] = m->tmN[i]; maps.tmE[i] = m->tmE[i];
+        maps.tsW[i] = m->tsW[i]; maps.tsN[i] = m->tsN[i]; maps.tsE[i] = m->tsE[i];
+    }
+    maps.tmD = m->tmD; maps.tmL = m->tmI.L; maps.tmR = m->tmI.R; maps.tmP = m->tmI.P;
+    const bool full = (m->D == 4 * LPP * VPL);
+#define HSM_LAUNCH_FLOW(T, F)                                                                                \
+    do {                                                                                                     \
+        auto kernel = k_iter_flow<LPP, VPL, NT, T, F>;                                                       \
+        CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
+        CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));         \
+        int per_sm = 0;                                                                                      \
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, NT, smem));                  \
+        const size_t resident = (size_t)std::max(per_sm, 1) * (size_t)m->sm_count;                           \
+        const unsigned grid = (unsigned)std::min(resident, tiles * (size_t)n_iter);                          \
+        if (getenv("HSM_FLOW_DEBUG"))                                                                        \
+            fprintf(stderr, "flow: grid %u (%d per SM), %d bands of %d rows x %d strips x %d frames, smem %zu, stages %d\n", \
+                    grid, per_sm, bands, a.band_rows, strips, m->frames, smem, stages);                      \
+        kernel<<<grid, NT, smem, m->stream>>>(maps, g, a, f, stages);                                        \
+    } while (0)
+    if (full) { if (dt_load) HSM_LAUNCH_FLOW(true, true); else HSM_LAUNCH_FLOW(false, true); }
+    else { if (dt_load) HSM_LAUNCH_FLOW(true, false); else HSM_LAUNCH_FLOW(false, false); }
+#undef HSM_LAUNCH_FLOW
+    HSM_TRY(check_launch(m, "k_iter_flow"));
+    m->stats.iteration_launches++;
+    m->cur = (m->cur + n_iter) & 1;
+    *launched = true;
+    return HSM_OK;
+}
+
+}  // namespace
+
+int launch_flow_any(hsm_matcher *m, int n_iter, bool finalize, bool *launched)
+{
+    HSM_DISPATCH(m->cfg, { return launch_flow<LPP, VPL, NT>(m, n_iter, finalize, launched); });
+    return fail(HSM_ERR_ARG, "no lane configuration");
+}
+
+}  // namespace hsm

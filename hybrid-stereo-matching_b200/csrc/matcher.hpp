@@ -112,6 +112,9 @@ struct hsm_matcher {
     int frame_groups = 0;                        // HSM_OPT_FRAME_GROUPS: 0 = automatic, 1 = one launch per iteration
     int launch_frame0 = 0, launch_frames = 0;
     cudaStream_t launch_stream = nullptr, aux_stream = nullptr;
+    unsigned *flow_state = nullptr;              // persistent dataflow kernel: task counter + per-tile progress
+    size_t flow_bytes = 0;
+    int sm_count = 148;
     bool launch_pdl = false;                     // programmatic dependent launch (one kernel per iteration only)
     cudaEvent_t fork_event = nullptr, join_event = nullptr;                 // iterations completed since hsm_peer_reset
     // statistics
@@ -154,6 +157,9 @@ int launch_tma_push_any(hsm_matcher *m, bool store_s);                 // same, 
 int launch_tma2_any(hsm_matcher *m, bool store_s, bool *launched);
 int launch_ws_any(hsm_matcher *m, bool store_s);
 int launch_tmast_any(hsm_matcher *m, bool store_s, bool *launched);
+// all n_iter iterations in one persistent launch (algorithm 6); *launched = false -> caller falls back
+int launch_flow_any(hsm_matcher *m, int n_iter, bool finalize, bool *launched);
+int choose_flow_band_rows(const hsm_matcher *m, int strips, int ctas_per_sm);
 int launch_tmast_push_any(hsm_matcher *m, bool store_s, bool *launched);
 
 }  // namespace hsm

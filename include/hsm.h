@@ -59,7 +59,11 @@ extern "C" {
                                      (falls back to 2 for an odd leftover / unsupported shapes),
                                  4 = like 2 with a TMA producer warp and warp-to-warp exchange (no CTA barrier),
                                  5 = like 2 with TMA stores (results staged in shared memory; DEFAULT; falls
-                                     back to 2 when the staging does not fit in shared memory, e.g. n_levels 256) */
+                                     back to 2 when the staging does not fit in shared memory, e.g. n_levels 256),
+                                 6 = persistent dataflow: all iterations of an hsm_iterate call in ONE launch of
+                                     kernel 5's code; (iteration, band, strip) tasks are ordered by per-tile
+                                     progress counters in global memory (falls back to 5).  With the default 5
+                                     it is chosen automatically for a single frame of >= 8M elements         */
 #define HSM_OPT_BAND_ROWS 1   /* rows per CTA band in the fused kernel; 0 = heuristic                */
 #define HSM_OPT_DATA_TERM 2   /* 0 = read the data plane (T28), 1 = recompute it in-kernel (T24, default) */
 #define HSM_OPT_VALID_LO 3    /* row-band mode: first/last local row that is inside the image ...    */

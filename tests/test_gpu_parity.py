@@ -15,8 +15,8 @@ ALL = [(c, True) for c in C.SMALL_CASES] + [(c, False) for c in C.BIG_CASES]
 IDS = [c["name"] for c, _ in ALL]
 # (algorithm, data_term): TMA-fed fused kernel with recomputed data term (default) / with the data plane,
 # LDG-fed fused kernel (both), one kernel per direction
-VARIANTS = [(5, 1), (5, 0), (4, 1), (4, 0), (3, 1), (2, 1), (2, 0), (1, 1), (1, 0), (0, 0)]
-VARIANT_IDS = ["tmast_T24", "tmast_T28", "ws_T24", "ws_T28", "tma2_T12", "tma_T24", "tma_T28", "ldg_T24", "ldg_T28",
+VARIANTS = [(6, 1), (6, 0), (5, 1), (5, 0), (4, 1), (4, 0), (3, 1), (2, 1), (2, 0), (1, 1), (1, 0), (0, 0)]
+VARIANT_IDS = ["flow_T24", "flow_T28", "tmast_T24", "tmast_T28", "ws_T24", "ws_T28", "tma2_T12", "tma_T24", "tma_T28", "ldg_T24", "ldg_T28",
                "directional_T80"]
 
 
@@ -51,10 +51,10 @@ def test_cuda_matches_reference_fixture(hsm, case, small, variant):
         assert C.plane_sha1(plane) == meta["plane_sha1"][name], name
 
 
-@pytest.mark.parametrize("band_rows", [1, 2, 5, 7])
+@pytest.mark.parametrize("band_rows", [1, 2, 3, 4, 5, 7])
 def test_band_height_does_not_change_results(hsm, band_rows):
     for case in (C.SMALL_CASES[3], C.SMALL_CASES[12], C.SMALL_CASES[24]):
-        labels, planes = C.run_case(_factory(hsm, {1: 3, 2: 5, 5: 4, 7: 2}[band_rows], 1, band_rows=band_rows), case)
+        labels, planes = C.run_case(_factory(hsm, {1: 3, 2: 5, 3: 6, 4: 6, 5: 4, 7: 2}[band_rows], 1, band_rows=band_rows), case)
         data, _ = C.load_fixture(case)
         assert np.array_equal(labels, data["labels"])
         for name, plane in planes.items():
@@ -122,7 +122,7 @@ def test_batch_equals_single_frames(hsm):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("algorithm", [5, 4, 2, 1])
+@pytest.mark.parametrize("algorithm", [6, 5, 4, 2, 1])
 def test_frame_groups_do_not_change_results(hsm, algorithm):
     """Two concurrent frame groups (HSM_OPT_FRAME_GROUPS = 2, the default for real workloads) == one
     launch per iteration == single frames, for odd and even frame counts."""

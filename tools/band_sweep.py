@@ -13,10 +13,12 @@ SWEEP = [
     ("270,1920,256,1,20", (15, 18, 23, 27, 34, 45, 68)),
     ("135,1920,256,1,20", (15, 18, 23, 27, 34, 45, 68)),
 ]
+SWEEP += [("480,640,64,1,50", (6, 8, 10, 12, 14, 16, 20)), ("180,240,32,1,50", (2, 3, 4, 5, 6)),
+          ("60,80,22,1,10", (2, 3, 4, 6))]
 if len(sys.argv) > 1:                      # python tools/band_sweep.py 3,4  -> only those entries
     SWEEP = [SWEEP[int(i)] for i in sys.argv[1].split(",")]
 for shape, bands in SWEEP:
     for br in (0,) + tuple(bands):
-        out = subprocess.run([sys.executable, os.path.join(HERE, "perf_probe.py"), "--only", "%s,5,1,%d,0" % (shape, br)],
+        out = subprocess.run([sys.executable, os.path.join(HERE, "perf_probe.py"), "--only", "%s,%s,1,%d,0" % (shape, os.environ.get("HSM_SWEEP_ALGO", "5"), br)],
                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT, universal_newlines=True).stdout
         print(out.strip().splitlines()[-1], flush=True)
