@@ -27,8 +27,25 @@ struct FlowArgs {
     int n_iter, frames, bands, strips;
     int cur;                                    // plane generation iteration 0 reads
     int finalize;                               // the last iteration also stores S'
+    // Row-band mode with neighbours on other GPUs (PUSH kernels): the tiles across a band boundary live in
+    // another launch on another GPU.  Their progress arrives in `ghost_in` (this GPU's memory, written by the
+    // neighbour; absolute iteration numbers since hsm_peer_reset, `base` = this launch's first), ours goes to
+    // `ghost_out` (the neighbour's memory).  `mail_in[side]` is the neighbour's whole-iteration counter of the
+    // one-launch-per-iteration path, which also satisfies a dependency.
+    const unsigned *ghost_in[2];
+    const unsigned *mail_in;
+    unsigned *ghost_out[2];
+    unsigned base;
+    float *pushW[2][2], *pushN[2][2], *pushE[2][2];   // [side][plane generation]
+    unsigned push_off[2];
 };
 
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned *p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ unsigned long long global_ns()
 {
     unsigned long long t;
@@ -37,10 +54,10 @@ __device__ __forceinline__ unsigned long long global_ns()
 }
 
 #ifndef HSM_FLOW_TIMEOUT_NS
-#define HSM_FLOW_TIMEOUT_NS 4000000000ull       // a dependency that takes 4 s is a bug: trap instead of hanging
+#define HSM_FLOW_TIMEOUT_NS 8000000000ull       // a dependency that takes 8 s is a bug: trap instead of hanging
 #endif
 
-template <int LPP, int VPL, int NT, bool DT_LOAD, bool FULL>
+template <int LPP, int VPL, int NT, bool DT_LOAD, bool FULL, bool PUSH>
 __global__ void __launch_bounds__(NT, NT == 256 ? (VPL == 1 ? HSM_TMA_MIN_BLOCKS : (VPL == 2 ? 2 : 1)) : 1)
     k_iter_flow(const __grid_constant__ FlowMaps maps, Geo g, IterArgs a, FlowArgs f, int stages)
 {
@@ -64,9 +81,10 @@ __global__ void __launch_bounds__(NT, NT == 256 ? (VPL == 1 ? HSM_TMA_MIN_BLOCKS
     int stage = 0;
     uint32_t phase = 0;
     bool first = true;
-    // the tile this CTA finished last and has not published yet (see flow_publish)
-    unsigned *pending = nullptr;
-    unsigned pending_value = 0;
+    // the tile this CTA finished last and has not published yet (see flow_publish); thread 0 owns it
+    FlowPending pending;
+    pending.local = nullptr; pending.remote[0] = pending.remote[1] = nullptr;
+    pending.local_value = pending.remote_value = 0;
     int pending_it = 0;
     if (tid == 0) s_next[0] = atomicAdd(f.counter, 1u);
     __syncthreads();
@@ -79,31 +97,46 @@ __global__ void __launch_bounds__(NT, NT == 256 ? (VPL == 1 ? HSM_TMA_MIN_BLOCKS
         unsigned rem = task - (unsigned)it * per_iter;
         const int frame = (int)(rem / per_frame);
         rem -= (unsigned)frame * per_frame;
-        const int by = (int)(rem / (unsigned)f.strips);
-        const int bx = (int)(rem - (unsigned)by * (unsigned)f.strips);
+        const int pos = (int)(rem / (unsigned)f.strips);       // position of the band in the hand-out order
+        const int bx = (int)(rem - (unsigned)pos * (unsigned)f.strips);
+        // Row bands over several GPUs: the neighbouring GPUs wait for this band's first and last tile rows, so
+        // those go first and the order runs from both ends inwards (0, B-1, 1, B-2, ...); a tile's neighbours of
+        // the previous iteration are still handed out about one iteration's worth of tiles before it.
+        const int by = !PUSH ? pos : ((pos & 1) ? f.bands - 1 - (pos >> 1) : (pos >> 1));
         unsigned *tile = f.done + (size_t)frame * per_frame;
         // a tile of a later iteration may depend on the unpublished one (possibly only on it): publish first
-        if (pending != nullptr && it > pending_it) {
-            if (tid == 0) flow_publish(pending, pending_value);
-            pending = nullptr;
+        if (pending.local != nullptr && it > pending_it) {
+            if (tid == 0) flow_publish<PUSH>(pending);
+            pending.local = nullptr;
         }
-        if (it > 0 && tid < 32) {                // warp 0: nine pollers, one neighbouring tile each
+        if (tid < 32) {                          // warp 0: nine pollers, one neighbouring tile each
             const int nb = by + tid / 3 - 1, ns = bx + tid % 3 - 1;
-            const bool polls = tid < 9 && nb >= 0 && nb < f.bands && ns >= 0 && ns < f.strips;
-            const unsigned *flag = tile + (polls ? nb * f.strips + ns : 0);
-            bool waits = polls && ld_acquire_gpu(flag) < (unsigned)it;
+            const bool in_s = tid < 9 && ns >= 0 && ns < f.strips;
+            const bool local = in_s && it > 0 && nb >= 0 && nb < f.bands;
+            // across the band boundary: the neighbouring GPU's tile (PUSH kernels only)
+            const int side = nb < 0 ? 0 : 1;
+            const bool ghost = PUSH && in_s && (nb < 0 || nb >= f.bands) && f.ghost_in[side] != nullptr &&
+                               f.base + (unsigned)it > 0u;
+            const unsigned *flag = local ? tile + nb * f.strips + ns : (ghost ? f.ghost_in[side] + ns : f.done);
+            const unsigned need = local ? (unsigned)it : f.base + (unsigned)it;
+            auto ready = [&]() -> bool {
+                if (local) return ld_acquire_gpu(flag) >= need;
+                if (ghost) return ld_acquire_sys(flag) >= need || ld_acquire_sys(f.mail_in + side) >= need;
+                return true;
+            };
+            const bool waits = !ready();
             if (__any_sync(0xffffffffu, waits)) {
-                // not ready yet: do not sit on our own finished tile while we wait (thread 0 owns `pending`)
-                if (tid == 0 && pending != nullptr) {
-                    flow_publish(pending, pending_value);
-                    pending = nullptr;
+                // not ready yet: do not sit on our own finished tile while we wait
+                if (tid == 0 && pending.local != nullptr) {
+                    flow_publish<PUSH>(pending);
+                    pending.local = nullptr;
                 }
                 if (waits) {
                     const unsigned long long t0 = global_ns();
                     do {
                         __nanosleep(32);
                         if (global_ns() - t0 > HSM_FLOW_TIMEOUT_NS) __trap();
-                    } while (ld_acquire_gpu(flag) < (unsigned)it);
+                    } while (!ready());
                 }
             }
         }
@@ -112,21 +145,33 @@ __global__ void __launch_bounds__(NT, NT == 256 ? (VPL == 1 ? HSM_TMA_MIN_BLOCKS
         if (tid == 0) asm volatile("fence.proxy.async;" ::: "memory");
         const int in = (f.cur + it) & 1, out = in ^ 1;
         const bool store_s = f.finalize != 0 && it == f.n_iter - 1;
-        tmast_task<LPP, VPL, NT, DT_LOAD, FULL, false, true>(&maps.tmW[in], &maps.tmN[in], &maps.tmE[in], &maps.tmD,
-                                                             &maps.tmL, &maps.tmR, &maps.tmP, &maps.tsW[out],
-                                                             &maps.tsN[out], &maps.tsE[out], g, a, stages, bx, by, frame,
-                                                             store_s, smem_raw, stage, phase, first, pending,
-                                                             pending_value);
+        PushPtrs pp;
+#pragma unroll
+        for (int side = 0; side < 2; ++side) {
+            pp.W[side] = PUSH ? f.pushW[side][out] : nullptr;
+            pp.N[side] = PUSH ? f.pushN[side][out] : nullptr;
+            pp.E[side] = PUSH ? f.pushE[side][out] : nullptr;
+            pp.off[side] = f.push_off[side];
+        }
+        tmast_task<LPP, VPL, NT, DT_LOAD, FULL, PUSH, true>(&maps.tmW[in], &maps.tmN[in], &maps.tmE[in], &maps.tmD,
+                                                            &maps.tmL, &maps.tmR, &maps.tmP, &maps.tsW[out],
+                                                            &maps.tsN[out], &maps.tsE[out], g, a, stages, bx, by, frame,
+                                                            store_s, smem_raw, stage, phase, first, pp, &pending);
         first = false;
-        pending = tile + by * f.strips + bx;
-        pending_value = (unsigned)it + 1u;
+        pending.local = tile + by * f.strips + bx;
+        pending.local_value = (unsigned)it + 1u;
+        pending.remote_value = f.base + (unsigned)it + 1u;
+        pending.remote[0] = (PUSH && by == 0 && f.ghost_out[0] != nullptr) ? f.ghost_out[0] + bx : nullptr;
+        pending.remote[1] = (PUSH && by == f.bands - 1 && f.ghost_out[1] != nullptr) ? f.ghost_out[1] + bx : nullptr;
         pending_it = it;
-        if (store_s) __threadfence();            // S' of the last iteration went out with plain stores
+        // plain stores of every thread: S' of the last iteration, boundary rows pushed to the neighbours
+        if (PUSH && (pending.remote[0] != nullptr || pending.remote[1] != nullptr)) __threadfence_system();
+        else if (store_s) __threadfence();
         __syncthreads();
         task = s_next[slot];
         slot ^= 1;
     }
-    if (pending != nullptr && tid == 0) flow_publish(pending, pending_value);
+    if (pending.local != nullptr && tid == 0) flow_publish<PUSH>(pending);
 }
 
 }  // namespace hsm

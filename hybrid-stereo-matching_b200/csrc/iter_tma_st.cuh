@@ -29,14 +29,33 @@ __device__ __forceinline__ void st_release_gpu(unsigned *p, unsigned v)
 {
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-// Dataflow kernel: publish a finished tile.  Called by the thread that issued the tile's bulk stores, once they
-// are no longer needed in flight: wait for their completion, then release the tile's progress counter.
-__device__ __forceinline__ void flow_publish(unsigned *flag, unsigned value)
+// Dataflow kernel: a finished tile waiting to be published -- its local progress counter and, for a tile on
+// the band's boundary in row-band mode, the counters in the neighbouring GPUs' memory.
+struct FlowPending {
+    unsigned *local;            // nullptr = nothing pending
+    unsigned local_value;
+    unsigned *remote[2];        // nullptr = no neighbour on that side / not a boundary tile
+    unsigned remote_value;
+};
+__device__ __forceinline__ void st_release_sys(unsigned *p, unsigned v)
+{
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// Called by the thread that issued the tile's bulk stores, once they are no longer needed in flight: wait for
+// their completion, then release the counters.  (Peer pushes were plain stores of all threads, fenced at
+// system scope by each thread before the CTA barrier that precedes this call.)
+template <bool PUSH>
+__device__ __forceinline__ void flow_publish(const FlowPending &p)
 {
     tma_store_wait_all();
     asm volatile("fence.proxy.async;" ::: "memory");
-    __threadfence();
-    st_release_gpu(flag, value);
+    if (PUSH && (p.remote[0] != nullptr || p.remote[1] != nullptr)) __threadfence_system();
+    else __threadfence();
+    st_release_gpu(p.local, p.local_value);
+    if (PUSH) {
+        if (p.remote[0]) st_release_sys(p.remote[0], p.remote_value);
+        if (p.remote[1]) st_release_sys(p.remote[1], p.remote_value);
+    }
 }
 
 // One task of the fused iteration: strip `bx`, band `by` of frame `frame`.  Shared by the one-launch-per-
@@ -50,7 +69,7 @@ __device__ __forceinline__ void tmast_task(const CUtensorMap *tmW, const CUtenso
                                            const CUtensorMap *tsE, const Geo &g, const IterArgs &a, const int stages,
                                            const int bx, const int by, const int frame, const bool STORE_S,
                                            unsigned char *smem_raw, int &stage, uint32_t &phase, const bool first_task,
-                                           unsigned *publish_flag = nullptr, unsigned publish_value = 0)
+                                           const PushPtrs &pp, const FlowPending *publish = nullptr)
 {
     using SL = StageLayout<LPP, VPL, NT>;
     constexpr int PX = NT / LPP;
@@ -137,7 +156,7 @@ __device__ __forceinline__ void tmast_task(const CUtensorMap *tmW, const CUtenso
         }
         // dataflow kernel: the previous tile of this CTA is published only now, so that the completion
         // of its stores overlaps this tile's dependency wait and first loads
-        if (FLOW && publish_flag) flow_publish(publish_flag, publish_value);
+        if (FLOW && publish && publish->local) flow_publish<PUSH>(*publish);
     }
 
     float *Sout = a.Sout + fplane;
@@ -212,8 +231,8 @@ __device__ __forceinline__ void tmast_task(const CUtensorMap *tmW, const CUtenso
     auto push_row = [&](float *const (&peer)[2], int row, int dx, bool mine, const Vec<VPL> &val) {
         if (!mine) return;
         const unsigned col = lane_col + (unsigned)(dx * g.Dp);
-        if (row == a.olo && peer[0] != nullptr) store_at(peer[0], a.push_off[0] + col, val);
-        if (row == a.ohi && peer[1] != nullptr) store_at(peer[1], a.push_off[1] + col, val);
+        if (row == a.olo && peer[0] != nullptr) store_at(peer[0], pp.off[0] + col, val);
+        if (row == a.ohi && peer[1] != nullptr) store_at(peer[1], pp.off[1] + col, val);
     };
 
     // row yb0-1 only contributes S'(yb0)
@@ -272,7 +291,7 @@ __device__ __forceinline__ void tmast_task(const CUtensorMap *tmW, const CUtenso
 #pragma unroll
         for (int v = 0; v < VPL; ++v) ex(par, v, tid) = t.q[v];
         if (st_w) stage_out(st_wp, par, t);
-        if constexpr (PUSH) push_row(a.pushW, y, -1, st_w && (x - 1) < g.W && y <= yb1, t);
+        if constexpr (PUSH) push_row(pp.W, y, -1, st_w && (x - 1) < g.W && y <= yb1, t);
         if (STORE_S && st_s && y + 1 <= yb1) store_at(Sout, row_off + row_stride, Snext);
         // staging writes (this row's W', the previous row's N', E') -> visible to the async proxy
         tma_store_fence();
@@ -318,8 +337,8 @@ __device__ __forceinline__ void tmast_task(const CUtensorMap *tmW, const CUtenso
         if (upper) {
             if (st_n) stage_out(st_np, par, tn);
             if (st_e) stage_out(st_ep, par, t);
-            if constexpr (PUSH) push_row(a.pushN, y - 1, 0, st_n && in_x, tn);
-            if constexpr (PUSH) push_row(a.pushE, y - 1, +1, st_e && (x + 1) < g.W, t);
+            if constexpr (PUSH) push_row(pp.N, y - 1, 0, st_n && in_x, tn);
+            if constexpr (PUSH) push_row(pp.E, y - 1, +1, st_e && (x + 1) < g.W, t);
         }
         row_off += row_stride;
     };
@@ -355,10 +374,15 @@ __global__ void __launch_bounds__(NT, (NT == 256 && VPL == 1) ? HSM_TMA_MIN_BLOC
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     int stage = 0;
     uint32_t phase = 0;
+    PushPtrs pp;
+    for (int side = 0; side < 2; ++side) {
+        pp.W[side] = a.pushW[side]; pp.N[side] = a.pushN[side]; pp.E[side] = a.pushE[side];
+        pp.off[side] = a.push_off[side];
+    }
     tmast_task<LPP, VPL, NT, DT_LOAD, FULL, PUSH, false>(&tmW, &tmN, &tmE, &tmD, &tmL, &tmR, &tmP, &tsW, &tsN, &tsE, g,
                                                          a, stages, (int)blockIdx.x, (int)blockIdx.y,
                                                          a.frame0 + (int)blockIdx.z, a.store_s != 0, smem_raw, stage,
-                                                         phase, true);
+                                                         phase, true, pp);
 }
 
 }  // namespace hsm

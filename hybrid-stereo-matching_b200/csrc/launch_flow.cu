@@ -1,4 +1,10 @@
 // Launch code of the persistent dataflow kernel (see iter_flow.cuh, matcher.hpp).
+// Compiled twice: as is, and through launch_flow_push.cu with HSM_PUSH = true for row bands whose neighbours
+// live on other GPUs (boundary rows and progress counters go through peer-mapped memory).
+#ifndef HSM_PUSH
+#define HSM_PUSH false
+#define HSM_FLOW_ENTRY launch_flow_any
+#endif
 #include "matcher.hpp"
 #include "iter_flow.cuh"
 
@@ -47,6 +53,21 @@ int launch_flow(hsm_matcher *m, int n_iter, bool finalize, bool *launched)
     f.counter = m->flow_state; f.done = m->flow_state + 1;
     f.n_iter = n_iter; f.frames = m->frames; f.bands = bands; f.strips = strips;
     f.cur = m->cur; f.finalize = finalize ? 1 : 0;
+    f.base = m->p2p_iterations;
+    f.mail_in = m->mailbox;
+    if (HSM_PUSH && strips > hsm_matcher::kGhostStride) return HSM_OK;
+    for (int side = 0; side < 2; ++side) {
+        const hsm_matcher::Peer &p = m->peer[side];
+        const bool on = HSM_PUSH && p.attached;
+        f.ghost_in[side] = on ? m->mailbox + hsm_matcher::kGhostBase + side * hsm_matcher::kGhostStride : nullptr;
+        f.ghost_out[side] = on ? p.ghost_flags : nullptr;
+        for (int gen = 0; gen < 2; ++gen) {
+            f.pushW[side][gen] = on ? p.Wm[gen] : nullptr;
+            f.pushN[side][gen] = on ? p.Nm[gen] : nullptr;
+            f.pushE[side][gen] = on ? p.Em[gen] : nullptr;
+        }
+        f.push_off[side] = p.ghost_off;
+    }
     FlowMaps maps;
     for (int i = 0; i < 2; ++i) {
         maps.tmW[i] = m->tmW[i]; maps.tmN[i] = m->tmN[i]; maps.tmE[i] = m->tmE[i];
@@ -56,7 +77,7 @@ int launch_flow(hsm_matcher *m, int n_iter, bool finalize, bool *launched)
     const bool full = (m->D == 4 * LPP * VPL);
 #define HSM_LAUNCH_FLOW(T, F)                                                                                \
     do {                                                                                                     \
-        auto kernel = k_iter_flow<LPP, VPL, NT, T, F>;                                                       \
+        auto kernel = k_iter_flow<LPP, VPL, NT, T, F, HSM_PUSH>;                                                       \
         CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
         CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));         \
         int per_sm = 0;                                                                                      \
@@ -80,7 +101,7 @@ int launch_flow(hsm_matcher *m, int n_iter, bool finalize, bool *launched)
 
 }  // namespace
 
-int launch_flow_any(hsm_matcher *m, int n_iter, bool finalize, bool *launched)
+int HSM_FLOW_ENTRY(hsm_matcher *m, int n_iter, bool finalize, bool *launched)
 {
     HSM_DISPATCH(m->cfg, { return launch_flow<LPP, VPL, NT>(m, n_iter, finalize, launched); });
     return fail(HSM_ERR_ARG, "no lane configuration");

@@ -1,0 +1,5 @@
+// The persistent dataflow kernels with the peer-to-peer halo push and cross-GPU progress counters compiled in
+// (row-band mode, hsm_peer_attach).
+#define HSM_PUSH true
+#define HSM_FLOW_ENTRY launch_flow_push_any
+#include "launch_flow.cu"

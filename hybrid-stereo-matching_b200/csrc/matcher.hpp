@@ -103,8 +103,14 @@ struct hsm_matcher {
         float *Wm[2] = {nullptr, nullptr}, *Nm[2] = {nullptr, nullptr}, *Em[2] = {nullptr, nullptr};
         unsigned *mailbox = nullptr;             // the slot of the neighbour's mailbox this matcher writes
         unsigned ghost_off = 0;                  // element offset of the neighbour's ghost row inside its planes
+        unsigned *ghost_flags = nullptr;         // dataflow kernel: per-strip progress counters in the neighbour's
+                                                 // mailbox region that this matcher's boundary tiles publish to
     } peer[2];
-    unsigned *mailbox = nullptr;                 // [0] written by the band above, [1] by the band below
+    // mailbox region in the arena (visible to the neighbours through the IPC mapping):
+    //   [0], [1]                     whole-iteration counters written by the band above / below (stream-ordered)
+    //   [kGhostBase + side * kGhostStride + strip]   per-strip progress of the neighbour's boundary tiles
+    static constexpr int kGhostBase = 64, kGhostStride = 1024, kMailboxWords = kGhostBase + 2 * kGhostStride;
+    unsigned *mailbox = nullptr;
     unsigned p2p_iterations = 0;
     // Frame groups: an iteration over >= 2 frames is launched as two kernels (first / second half of the
     // frames) on two streams, so that one group's tail (SMs idling while the last CTAs finish) is filled by
@@ -159,6 +165,7 @@ int launch_ws_any(hsm_matcher *m, bool store_s);
 int launch_tmast_any(hsm_matcher *m, bool store_s, bool *launched);
 // all n_iter iterations in one persistent launch (algorithm 6); *launched = false -> caller falls back
 int launch_flow_any(hsm_matcher *m, int n_iter, bool finalize, bool *launched);
+int launch_flow_push_any(hsm_matcher *m, int n_iter, bool finalize, bool *launched);   // with neighbours attached
 int choose_flow_band_rows(const hsm_matcher *m, int strips, int ctas_per_sm);
 int launch_tmast_push_any(hsm_matcher *m, bool store_s, bool *launched);
 
