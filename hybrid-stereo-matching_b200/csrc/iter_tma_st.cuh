@@ -107,6 +107,10 @@ __device__ __forceinline__ void tmast_task(const CUtensorMap *tmW, const CUtenso
     const bool st_e = px <= PX - 3;                            // E'(y-1, x+1)-> staging slot px
     const bool st_s = in_x && px >= 1 && px <= PX - 2;         // S' goes out with plain stores (last iteration only)
     const int rd_slot = (x < 0) ? (NT + LPP + ln.c) : (tid + LPP);
+    // W' exchange slots of this lane as shared-space addresses: [parity][v] are constant offsets from these
+    const unsigned ex_wr_addr = smem_u32(exch) + 16u * (unsigned)tid;
+    const unsigned ex_rd_addr = smem_u32(exch) + 16u * (unsigned)rd_slot;
+    constexpr unsigned EX_V = SLOTS * 16u, EX_PAR = VPL * SLOTS * 16u;
 
     if (first_task) {
         if (tid == 0) {
@@ -185,7 +189,11 @@ __device__ __forceinline__ void tmast_task(const CUtensorMap *tmW, const CUtenso
     const unsigned lane_f4 = (unsigned)px * (unsigned)(g.Dp / 4) + (unsigned)ln.c;   // float4 index in a row segment
     const unsigned plane_f4 = row_floats / 4;
     const float4 *lane_base = reinterpret_cast<const float4 *>(smem_raw) + lane_f4;
-    const unsigned char *img_base = smem_raw + planes_bytes;
+    // shared-space addresses of this lane's image / prior entries inside stage 0 (see data_vec_lds)
+    const unsigned img_addr = smem_u32(smem_raw) + planes_bytes;
+    const unsigned l_addr = img_addr + 4u * (unsigned)(shift_l + px);
+    const unsigned r_addr = img_addr + SL::L_BYTES + 4u * (unsigned)(shift_r + px - 1 + SL::DCOV - ln.chunk_offset(0));
+    const unsigned p_addr = img_addr + SL::L_BYTES + SL::R_BYTES + 4u * (unsigned)(shift_l + px);
     // element offset of (row y, this lane's pixel and chunk) inside the frame; advanced by one row per step
     // (x may be -1 or W for halo lanes: the wrap-around cancels when the neighbour offset is added)
     unsigned row_off = (unsigned)yb0 * row_stride + (unsigned)x * (unsigned)g.Dp + 4u * (unsigned)ln.c;
@@ -207,13 +215,9 @@ __device__ __forceinline__ void tmast_task(const CUtensorMap *tmW, const CUtenso
                 if (DT_LOAD) d.q[v] = zero4();
             }
         }
-        if (!DT_LOAD) {
-            const unsigned char *img = img_base + stage_off;
-            data_vec_smem<LPP, VPL, FULL>(d, ln, reinterpret_cast<const float *>(img) + shift_l,
-                                          reinterpret_cast<const float *>(img + SL::L_BYTES) + shift_r,
-                                          reinterpret_cast<const int *>(img + SL::L_BYTES + SL::R_BYTES) + shift_l, px,
-                                          x, in_x, g.D, a.blend, a.has_prior != 0);
-        }
+        if (!DT_LOAD)
+            data_vec_lds<LPP, VPL, FULL>(d, ln, l_addr + stage_off, r_addr + stage_off, p_addr + stage_off, x, in_x,
+                                         g.D, a.blend, a.has_prior != 0);
     };
     // every thread has copied the current stage: refill it with row index r + stages
     auto refill = [&](int r) {
@@ -289,7 +293,7 @@ __device__ __forceinline__ void tmast_task(const CUtensorMap *tmW, const CUtenso
             }
         }
 #pragma unroll
-        for (int v = 0; v < VPL; ++v) ex(par, v, tid) = t.q[v];
+        for (int v = 0; v < VPL; ++v) sts_f4(ex_wr_addr + par * EX_PAR + v * EX_V, t.q[v]);
         if (st_w) stage_out(st_wp, par, t);
         if constexpr (PUSH) push_row(pp.W, y, -1, st_w && (x - 1) < g.W && y <= yb1, t);
         if (STORE_S && st_s && y + 1 <= yb1) store_at(Sout, row_off + row_stride, Snext);
@@ -305,7 +309,7 @@ __device__ __forceinline__ void tmast_task(const CUtensorMap *tmW, const CUtenso
         }
         // X = S'(y, x) + W'(y, x)
 #pragma unroll
-        for (int v = 0; v < VPL; ++v) Xout.q[v] = add4(Sin.q[v], ex(par, v, rd_slot));
+        for (int v = 0; v < VPL; ++v) Xout.q[v] = add4(Sin.q[v], lds_f4(ex_rd_addr + par * EX_PAR + v * EX_V));
         // N'(y-1, x) = norm(U_N(y, x));  E'(y-1, x+1) = norm(U_E(y-1, x)) needs N'(y-1, x)
         Vec<VPL> tn;
 #pragma unroll
