@@ -56,6 +56,27 @@ def test_division_matches_ieee_full_exponent_range(hsm):
     assert _mismatches(a, b) == 0
 
 
+def test_fast_sequence_range(hsm):
+    """The unchecked sequence of normalise_fast() claims 2^-100 <= a <= m <= 2^26; the self-test kernel runs it
+    wherever that holds and compares with div.rn.f32.  Small numerators against ordinary and small maxima,
+    hard mantissas, and the corners of the range."""
+    rng = np.random.default_rng(7)
+    n = 1 << 21
+    for m_lo, m_hi in ((-2, 3), (-100, 26), (20, 26), (-100, -90)):
+        m = _random_floats(rng, n, m_lo, m_hi, signed=False)
+        m = np.minimum(m, np.float32(2.0 ** 26))
+        a = _random_floats(rng, 4 * n, -100, 26, signed=False).reshape(n, 4)
+        a = np.minimum(a, m[:, None])                      # numerators never exceed the max
+        a[:, 0] = np.where(rng.random(n) < 0.5, m, a[:, 0])   # the max itself is one of the numerators
+        assert _mismatches(a, m) == 0, (m_lo, m_hi)
+    # quotients just above the smallest normal number: a near 2^-100, m near 2^26
+    m = np.full(n, 2.0 ** 26, dtype=np.float32)
+    m[::2] = np.nextafter(m[::2], np.float32(0))
+    a = _random_floats(rng, 4 * n, -100, -98, signed=False).reshape(n, 4)
+    a[:, 3] = np.float32(2.0 ** -100)
+    assert _mismatches(a, m) == 0
+
+
 def test_division_special_values(hsm):
     specials = np.array([0.0, -0.0, 1.0, -1.0, np.inf, -np.inf, 1e-45, -1e-45, 1.1754944e-38, 3.4028235e38,
                          2.0 ** -60, 2.0 ** 60, np.nextafter(np.float32(2.0 ** -60), np.float32(0)),
