@@ -54,7 +54,8 @@ __device__ __forceinline__ unsigned long long global_ns()
 }
 
 #ifndef HSM_FLOW_TIMEOUT_NS
-#define HSM_FLOW_TIMEOUT_NS 8000000000ull       // a dependency that takes 8 s is a bug: trap instead of hanging
+#define HSM_FLOW_TIMEOUT_NS 30000000000ull      // the order of the tasks rules out a deadlock; should a dependency
+                                                 // still take 30 s something is badly wrong: trap instead of hanging
 #endif
 
 template <int LPP, int VPL, int NT, bool DT_LOAD, bool FULL, bool PUSH>
