@@ -92,6 +92,11 @@ __device__ __forceinline__ void tmast_task(const CUtensorMap *tmW, const CUtenso
     uint64_t *full = reinterpret_cast<uint64_t *>(exch + 2 * VPL * SLOTS);
     auto ex = [&](int par, int v, int slot) -> float4 & { return exch[(par * VPL + v) * SLOTS + slot]; };
 
+#ifdef HSM_EXPERIMENT_ALIAS_FRAMES
+    const int frame_mem = frame & 1;        // timing experiment only: every frame reads / writes frames 0, 1
+#else
+    const int frame_mem = frame;
+#endif
     const int xs0 = bx * TX;
     const int shift_l = (xs0 - 1) & 3, shift_r = (xs0 - SL::DCOV) & 3;    // see StageLayout
     const int x = xs0 - 1 + px;
@@ -132,9 +137,9 @@ __device__ __forceinline__ void tmast_task(const CUtensorMap *tmW, const CUtenso
         unsigned tx = NPL * row_floats * 4u;
         if (!DT_LOAD) tx += SL::LBOX * 4u + SL::NRB * SL::RBOX * 4u + (a.has_prior ? SL::LBOX * 4u : 0u);
         mbar_expect_tx(&full[s], tx);
-        tma_load_4d(dst, tmW, &full[s], 0, xs0 - 1, yy, frame);
-        tma_load_4d(dst + row_floats, tmN, &full[s], 0, xs0 - 1, yy, frame);
-        tma_load_4d(dst + 2 * row_floats, tmE, &full[s], 0, xs0 - 1, yy, frame);
+        tma_load_4d(dst, tmW, &full[s], 0, xs0 - 1, yy, frame_mem);
+        tma_load_4d(dst + row_floats, tmN, &full[s], 0, xs0 - 1, yy, frame_mem);
+        tma_load_4d(dst + 2 * row_floats, tmE, &full[s], 0, xs0 - 1, yy, frame_mem);
         if (DT_LOAD) {
             tma_load_4d(dst + 3 * row_floats, tmD, &full[s], 0, xs0 - 1, yy, frame);
         } else {
@@ -176,7 +181,7 @@ __device__ __forceinline__ void tmast_task(const CUtensorMap *tmW, const CUtenso
     };
     // thread 0: one bulk tensor store per plane-row; out-of-image columns are clipped by the TMA unit
     auto tma_store_row = [&](const CUtensorMap *map, int plane, int buf, int y) {
-        tma_store_4d(map, ost + (2u * plane + buf) * ost_bytes, 0, xs0, y - g.vlo, frame);
+        tma_store_4d(map, ost + (2u * plane + buf) * ost_bytes, 0, xs0, y - g.vlo, frame_mem);
     };
 
     // ---- consumer side ------------------------------------------------------------------------
