@@ -221,8 +221,8 @@ __device__ __forceinline__ void tmast_task(const CUtensorMap *tmW, const CUtenso
             }
         }
         if (!DT_LOAD)
-            data_vec_lds<LPP, VPL, FULL>(d, ln, l_addr + stage_off, r_addr + stage_off, p_addr + stage_off, x, in_x,
-                                         g.D, a.blend, a.has_prior != 0);
+            data_vec_lds<LPP, VPL, FULL>(d, ln, l_addr + stage_off, r_addr + stage_off, p_addr + stage_off,
+                                         in_x ? x : -1, g.D, a.blend, a.has_prior != 0);
     };
     // every thread has copied the current stage: refill it with row index r + stages
     auto refill = [&](int r) {
@@ -301,17 +301,22 @@ __device__ __forceinline__ void tmast_task(const CUtensorMap *tmW, const CUtenso
         for (int v = 0; v < VPL; ++v) sts_f4(ex_wr_addr + par * EX_PAR + v * EX_V, t.q[v]);
         if (st_w) stage_out(st_wp, par, t);
         if constexpr (PUSH) push_row(pp.W, y, -1, st_w && (x - 1) < g.W && y <= yb1, t);
-        if (STORE_S && st_s && y + 1 <= yb1) store_at(Sout, row_off + row_stride, Snext);
+        if (STORE_S) {                         // block-uniform: the last iteration only
+            if (st_s && y + 1 <= yb1) store_at(Sout, row_off + row_stride, Snext);
+        }
         // staging writes (this row's W', the previous row's N', E') -> visible to the async proxy
         tma_store_fence();
         if (tid == 0) tma_store_wait_read();   // the buffers about to be reused have been read by the TMA unit
         __syncthreads();                       // the row's only CTA barrier: W' published, stage consumed
-        refill(y - yb0 + 1);
+        // thread 0: refill the stage every thread has copied (row index r + stages), send this row's results
         if (tid == 0) {
+            const int r = y - yb0 + 1;
+            if (r + stages < n_rows) issue(r + stages, stage);
             if (y <= yb1) tma_store_row(tsW, 0, par, y);
             if (y > yb0 + 1) { tma_store_row(tsN, 1, par ^ 1, y - 2); tma_store_row(tsE, 2, par ^ 1, y - 2); }
             tma_store_commit();
         }
+        if (++stage == stages) { stage = 0; phase ^= 1u; }
         // X = S'(y, x) + W'(y, x)
 #pragma unroll
         for (int v = 0; v < VPL; ++v) Xout.q[v] = add4(Sin.q[v], lds_f4(ex_rd_addr + par * EX_PAR + v * EX_V));
