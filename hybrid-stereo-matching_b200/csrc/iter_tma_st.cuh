@@ -265,7 +265,8 @@ __device__ __forceinline__ void tmast_task(const CUtensorMap *tmW, const CUtenso
                     const Vec<VPL> &Din, Vec<VPL> &Dout) {
         Vec<VPL> w, n, e;
         fetch(w, n, e, Dout);
-        if (y > g.vhi) {                       // block-uniform: the row below the image sends nothing
+        if (__any_sync(0xffffffffu, y > g.vhi)) {   // block-uniform (the vote keeps it a branch, not four
+                                                    // selects per row): the row below the image sends nothing
 #pragma unroll
             for (int v = 0; v < VPL; ++v) Sin.q[v] = zero4();
         }
