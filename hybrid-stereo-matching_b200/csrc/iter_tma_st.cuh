@@ -114,7 +114,9 @@ __device__ __forceinline__ void tmast_task(const CUtensorMap *tmW, const CUtenso
     const int rd_slot = (x < 0) ? (NT + LPP + ln.c) : (tid + LPP);
     // W' exchange slots of this lane as shared-space addresses: [parity][v] are constant offsets from these
     const unsigned ex_wr_addr = smem_u32(exch) + 16u * (unsigned)tid;
-    const unsigned ex_rd_addr = smem_u32(exch) + 16u * (unsigned)rd_slot;
+    unsigned ex_rd_addr = smem_u32(exch) + 16u * (unsigned)rd_slot;
+    // keep it in a register: left alone, the compiler re-derives the slot from the thread index in every row
+    asm volatile("" : "+r"(ex_rd_addr));
     constexpr unsigned EX_V = SLOTS * 16u, EX_PAR = VPL * SLOTS * 16u;
 
     if (first_task) {
@@ -265,8 +267,7 @@ __device__ __forceinline__ void tmast_task(const CUtensorMap *tmW, const CUtenso
                     const Vec<VPL> &Din, Vec<VPL> &Dout) {
         Vec<VPL> w, n, e;
         fetch(w, n, e, Dout);
-        if (__any_sync(0xffffffffu, y > g.vhi)) {   // block-uniform (the vote keeps it a branch, not four
-                                                    // selects per row): the row below the image sends nothing
+        if (y > g.vhi) {                       // block-uniform: the row below the image sends nothing
 #pragma unroll
             for (int v = 0; v < VPL; ++v) Sin.q[v] = zero4();
         }
