@@ -379,7 +379,7 @@ __device__ __forceinline__ void tmast_task(const CUtensorMap *tmW, const CUtenso
 }
 
 template <int LPP, int VPL, int NT, bool DT_LOAD, bool FULL, bool PUSH>
-__global__ void __launch_bounds__(NT, (NT == 256 && VPL == 1) ? HSM_TMA_MIN_BLOCKS : 1)
+__global__ void __launch_bounds__(NT, NT == 256 ? (VPL == 1 ? HSM_TMA_MIN_BLOCKS : (VPL == 2 ? 2 : 1)) : 1)
     k_iter_tmast(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmN,
                const __grid_constant__ CUtensorMap tmE, const __grid_constant__ CUtensorMap tmD,
                const __grid_constant__ CUtensorMap tmL, const __grid_constant__ CUtensorMap tmR,
