@@ -1,4 +1,5 @@
-// Fused iteration kernel, TMA-fed variant (algorithm 2, the default).
+// Fused iteration kernel, TMA-fed variant (algorithm 2; the default, algorithm 5 in iter_tma_st.cuh, adds TMA
+// stores to this design and has received the later instruction-level work).
 //
 // Same arithmetic and the same row-streaming structure as k_iter_fused in
 // kernels.cuh (see the derivation there), but the old W / N / E (/ data) rows are

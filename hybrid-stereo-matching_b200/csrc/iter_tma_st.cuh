@@ -1,7 +1,11 @@
 // k_iter_tma with TMA STORES (algorithm 5): results are staged in shared memory and leave the SM
 // as one cp.async.bulk.tensor store per plane-row (issued by thread 0 after the row's barrier)
 // instead of per-thread STG.128 with 64-bit address arithmetic and edge predicates.  The TMA unit
-// clips columns >= W.  Everything else (arithmetic, pipeline, barrier) is k_iter_tma's.
+// clips columns >= W.  Arithmetic, pipeline and barrier structure are k_iter_tma's; this is the default kernel,
+// so the instruction-level work went here: shared-space addresses kept per lane, the data term's border / halo /
+// prior handling off the common path, warp-uniform branches instead of per-row selects.
+// The body is tmast_task(): one (strip, band, frame) tile of one iteration.  k_iter_tmast runs one task per CTA,
+// k_iter_flow (iter_flow.cuh) runs task after task in a persistent CTA.
 #pragma once
 
 #include "iter_tma.cuh"
