@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? (VPL == 1 ? HSM_TMA_MIN_BLOCKS
             pp.E[side] = PUSH ? f.pushE[side][out] : nullptr;
             pp.off[side] = f.push_off[side];
         }
-        tmast_task<LPP, VPL, NT, DT_LOAD, FULL, PUSH, true>(&maps.tmW[in], &maps.tmN[in], &maps.tmE[in], &maps.tmD,
+        tmast_task<LPP, VPL, NT, DT_LOAD, FULL, PUSH, true, 2>(&maps.tmW[in], &maps.tmN[in], &maps.tmE[in], &maps.tmD,
                                                             &maps.tmL, &maps.tmR, &maps.tmP, &maps.tsW[out],
                                                             &maps.tsN[out], &maps.tsE[out], g, a, stages, bx, by, frame,
                                                             store_s, smem_raw, stage, phase, first, pp, &pending);

@@ -66,12 +66,15 @@ __device__ __forceinline__ void flow_publish(const FlowPending &p)
 // iteration kernel (k_iter_tmast: one task per CTA) and the persistent dataflow kernel (iter_flow.cuh: a CTA
 // runs task after task; FLOW = true).  `stage` / `phase` are the position in the ring of row stages; they carry
 // over from task to task (every load issued by a task is consumed by it, so the ring stays consistent).
-template <int LPP, int VPL, int NT, bool DT_LOAD, bool FULL, bool PUSH, bool FLOW>
+// S_MODE: whether the tile also stores S' with plain stores (only the last iteration of a call does):
+// 0 = never, 1 = always, 2 = per call argument `store_s_arg` (the persistent kernel decides per task).  Compiled
+// out of the 49 of 50 launches that do not need it, the test costs nothing in their rows.
+template <int LPP, int VPL, int NT, bool DT_LOAD, bool FULL, bool PUSH, bool FLOW, int S_MODE>
 __device__ __forceinline__ void tmast_task(const CUtensorMap *tmW, const CUtensorMap *tmN, const CUtensorMap *tmE,
                                            const CUtensorMap *tmD, const CUtensorMap *tmL, const CUtensorMap *tmR,
                                            const CUtensorMap *tmP, const CUtensorMap *tsW, const CUtensorMap *tsN,
                                            const CUtensorMap *tsE, const Geo &g, const IterArgs &a, const int stages,
-                                           const int bx, const int by, const int frame, const bool STORE_S,
+                                           const int bx, const int by, const int frame, const bool store_s_arg,
                                            unsigned char *smem_raw, int &stage, uint32_t &phase, const bool first_task,
                                            const PushPtrs &pp, const FlowPending *publish = nullptr)
 {
@@ -80,6 +83,7 @@ __device__ __forceinline__ void tmast_task(const CUtensorMap *tmW, const CUtenso
     constexpr int TX = PX - 2;
     constexpr int SLOTS = NT + 2 * LPP;
     constexpr int NPL = DT_LOAD ? 4 : 3;
+    const bool STORE_S = S_MODE == 2 ? store_s_arg : (S_MODE == 1);
 
     const int tid = threadIdx.x;
     const int px = tid / LPP;
@@ -382,7 +386,7 @@ __device__ __forceinline__ void tmast_task(const CUtensorMap *tmW, const CUtenso
     }
 }
 
-template <int LPP, int VPL, int NT, bool DT_LOAD, bool FULL, bool PUSH>
+template <int LPP, int VPL, int NT, bool DT_LOAD, bool FULL, bool PUSH, bool STORE_S>
 __global__ void __launch_bounds__(NT, NT == 256 ? (VPL == 1 ? HSM_TMA_MIN_BLOCKS : (VPL == 2 ? 2 : 1)) : 1)
     k_iter_tmast(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmN,
                const __grid_constant__ CUtensorMap tmE, const __grid_constant__ CUtensorMap tmD,
@@ -399,10 +403,9 @@ __global__ void __launch_bounds__(NT, NT == 256 ? (VPL == 1 ? HSM_TMA_MIN_BLOCKS
         pp.W[side] = a.pushW[side]; pp.N[side] = a.pushN[side]; pp.E[side] = a.pushE[side];
         pp.off[side] = a.push_off[side];
     }
-    tmast_task<LPP, VPL, NT, DT_LOAD, FULL, PUSH, false>(&tmW, &tmN, &tmE, &tmD, &tmL, &tmR, &tmP, &tsW, &tsN, &tsE, g,
-                                                         a, stages, (int)blockIdx.x, (int)blockIdx.y,
-                                                         a.frame0 + (int)blockIdx.z, a.store_s != 0, smem_raw, stage,
-                                                         phase, true, pp);
+    tmast_task<LPP, VPL, NT, DT_LOAD, FULL, PUSH, false, STORE_S ? 1 : 0>(
+        &tmW, &tmN, &tmE, &tmD, &tmL, &tmR, &tmP, &tsW, &tsN, &tsE, g, a, stages, (int)blockIdx.x, (int)blockIdx.y,
+        a.frame0 + (int)blockIdx.z, STORE_S, smem_raw, stage, phase, true, pp);
 }
 
 }  // namespace hsm

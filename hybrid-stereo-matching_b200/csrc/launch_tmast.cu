@@ -42,7 +42,8 @@ int launch_tmast(hsm_matcher *m, bool store_s, bool *launched)
     cudaLaunchConfig_t cfg = launch_config(m, grid, NT, smem, &pdl_attr);
 #define HSM_LAUNCH_TMAST(T, F)                                                                               \
     do {                                                                                                     \
-        auto kernel = k_iter_tmast<LPP, VPL, NT, T, F, HSM_PUSH>;                                                      \
+        auto kernel = store_s ? k_iter_tmast<LPP, VPL, NT, T, F, HSM_PUSH, true>                             \
+                              : k_iter_tmast<LPP, VPL, NT, T, F, HSM_PUSH, false>;                           \
         CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
         CUDA_TRY(cudaLaunchKernelEx(&cfg, kernel, m->tmW[in], m->tmN[in], m->tmE[in], m->tmD, m->tmI.L, m->tmI.R,   \
                                     m->tmI.P, m->tsW[out], m->tsN[out], m->tsE[out], g, a, stages));           \
