@@ -634,9 +634,14 @@ int hsm_device_bytes(int rows, int cols, int n_levels, int capacity, size_t *byt
     return HSM_OK;
 }
 
-int hsm_init_fields(hsm_matcher *m, int n_frames, const void *left, const void *right, int image_dtype,
-                    const void *prior, int prior_dtype, int prior_mode, float keep_f32, double keep_f64,
-                    int reinit_messages, int on_device)
+}  // extern "C"
+
+namespace {
+// hsm_init_fields; `release_host` = the caller may reuse its host buffers when this returns (a stream
+// synchronisation, which hsm_lbp leaves to its readout)
+int init_fields_impl(hsm_matcher *m, int n_frames, const void *left, const void *right, int image_dtype,
+                     const void *prior, int prior_dtype, int prior_mode, float keep_f32, double keep_f64,
+                     int reinit_messages, int on_device, bool release_host)
 {
     if (!m) return fail(HSM_ERR_ARG, "null matcher");
     if (!left || !right) return fail(HSM_ERR_ARG, "null image pointer");
@@ -669,9 +674,20 @@ int hsm_init_fields(hsm_matcher *m, int n_frames, const void *left, const void *
     }
     m->have_fields = true;
     m->dt_valid = false;
-    // a pageable host buffer may be reused by the caller as soon as we return
-    if (!on_device) CUDA_TRY(cudaStreamSynchronize(m->stream));
+    // a host buffer may be reused by the caller as soon as we return
+    if (!on_device && release_host) CUDA_TRY(cudaStreamSynchronize(m->stream));
     return HSM_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int hsm_init_fields(hsm_matcher *m, int n_frames, const void *left, const void *right, int image_dtype,
+                    const void *prior, int prior_dtype, int prior_mode, float keep_f32, double keep_f64,
+                    int reinit_messages, int on_device)
+{
+    return init_fields_impl(m, n_frames, left, right, image_dtype, prior, prior_dtype, prior_mode, keep_f32, keep_f64,
+                            reinit_messages, on_device, true);
 }
 
 int hsm_iterate(hsm_matcher *m, int n_iter, int finalize)
@@ -827,8 +843,10 @@ int hsm_lbp(hsm_matcher *m, int n_frames, const void *left, const void *right, i
             int prior_dtype, int prior_mode, float keep_f32, double keep_f64, int n_iter, int64_t *labels,
             int on_device, int async)
 {
-    HSM_TRY(hsm_init_fields(m, n_frames, left, right, image_dtype, prior, prior_dtype, prior_mode, keep_f32,
-                            keep_f64, 1, on_device));
+    // one queue of work, one synchronisation (in the readout, unless async): with an asynchronous readout the
+    // host buffers must stay valid until hsm_sync, so only then are they released here
+    HSM_TRY(init_fields_impl(m, n_frames, left, right, image_dtype, prior, prior_dtype, prior_mode, keep_f32, keep_f64,
+                             1, on_device, async != 0));
     HSM_TRY(hsm_iterate(m, n_iter, 1));
     return hsm_readout(m, labels, on_device, async);
 }

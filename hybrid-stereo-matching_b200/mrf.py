@@ -150,11 +150,10 @@ class StereoMRF(object):
             assert image_right.shape == prior.shape                      # mrf.py:53
         return image_left, image_right, prior
 
-    def _init_fields(self, image_left, image_right, prior=None, prior_trust_factor=1.0,
-                     prior_influence_mode="adaptive", reinit_messages=True, _batched=False):
-        """Cost volume + optional prior blend + optional message reset (mrf.py:21-71)."""
-        image_left, image_right, prior = self._check_pair(image_left, image_right, prior, _batched)
-        n_frames = image_left.shape[0] if _batched else 1
+    def _host_inputs(self, image_left, image_right, prior, prior_trust_factor, prior_influence_mode, batched):
+        """The C ABI's view of the inputs: (n_frames, keep-alive arrays, argument tuple up to the blend)."""
+        image_left, image_right, prior = self._check_pair(image_left, image_right, prior, batched)
+        n_frames = image_left.shape[0] if batched else 1
         left, code = _as_image(image_left)
         right, code_r = _as_image(image_right)
         if code_r != code:
@@ -165,10 +164,17 @@ class StereoMRF(object):
         if prior is not None:
             prior, prior_code = _as_prior(prior)
             prior_ptr = prior.ctypes.data_as(ctypes.c_void_p)
-        _capi.check(_capi.lib().hsm_init_fields(
-            self._handle, n_frames, left.ctypes.data_as(ctypes.c_void_p),
-            right.ctypes.data_as(ctypes.c_void_p), code, prior_ptr, prior_code, mode,
-            keep32, keep64, 1 if reinit_messages else 0, 0))
+        args = (self._handle, n_frames, left.ctypes.data_as(ctypes.c_void_p), right.ctypes.data_as(ctypes.c_void_p),
+                code, prior_ptr, prior_code, mode, keep32, keep64)
+        return n_frames, (left, right, prior), args
+
+    def _init_fields(self, image_left, image_right, prior=None, prior_trust_factor=1.0,
+                     prior_influence_mode="adaptive", reinit_messages=True, _batched=False):
+        """Cost volume + optional prior blend + optional message reset (mrf.py:21-71)."""
+        n_frames, keep_alive, args = self._host_inputs(image_left, image_right, prior, prior_trust_factor,
+                                                       prior_influence_mode, _batched)
+        _capi.check(_capi.lib().hsm_init_fields(*args, 1 if reinit_messages else 0, 0))
+        del keep_alive
         self._frames, self._batched = n_frames, _batched
 
     def _update_message_fields(self):
@@ -200,12 +206,17 @@ class StereoMRF(object):
 
     def lbp(self, image_left, image_right, prior=None, prior_trust_factor=0.5,
             prior_influence_mode="const", n_iter=10):
-        """``loop_belief`` (always re-initialising) + ``get_map_belief`` (mrf.py:146-167)."""
-        self.loop_belief(image_left=image_left, image_right=image_right, prior=prior,
-                         prior_trust_factor=prior_trust_factor,
-                         prior_influence_mode=prior_influence_mode, n_iter=n_iter,
-                         reinit_messages=True)
-        return self.get_map_belief()
+        """``loop_belief`` (always re-initialising) + ``get_map_belief`` (mrf.py:146-167), as ONE native call:
+        upload, cost volume, ``n_iter`` iterations and readout are queued back to back and the host waits
+        once, for the labels."""
+        n_frames, keep_alive, args = self._host_inputs(image_left, image_right, prior, prior_trust_factor,
+                                                       prior_influence_mode, False)
+        labels = np.empty((1, self._rows, self._cols), dtype=np.int64)
+        _capi.check(_capi.lib().hsm_lbp(*args, int(n_iter), labels.ctypes.data_as(ctypes.c_void_p), 0, 0))
+        del keep_alive
+        self._frames, self._batched = n_frames, False
+        self._belief_field_cache = labels[0]
+        return self._belief_field_cache
 
     # ----------------------------------------------------------------- extensions
     def _lanes(self, count):
@@ -217,7 +228,7 @@ class StereoMRF(object):
         while len(lanes) < count - 1:
             helper = StereoMRF((self._rows, self._cols), self.n_levels, self.capacity, self.device)
             for key in (_capi.OPT_LANE_CONFIG, _capi.OPT_ALGORITHM, _capi.OPT_BAND_ROWS, _capi.OPT_DATA_TERM,
-                        _capi.OPT_STAGES):
+                        _capi.OPT_STAGES, _capi.OPT_FRAME_GROUPS):
                 helper.set_option(key, self.get_option(key))
             lanes.append(helper)
         return [self] + lanes[:count - 1]
