@@ -305,6 +305,7 @@ def main():
             "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": frames, "frames_per_launch": cap,
+                       "kernels_per_iteration": per_iter,
                        "sharding": "frames of the sequence dealt to ranks, no collective",
                        "l2": "inputs larger than L2: %.1f GB of message state per launch vs 126 MB"
                              % (6 * 4.0 * ROWS * COLS * LEVELS * cap / 1e9),
