@@ -46,9 +46,29 @@ def _sources():
         + [HEADER_PATH]
 
 
+STAMP_PATH = LIB_PATH + ".sources"      # sha256 of the sources the library was built from
+
+
+def _source_digest():
+    import hashlib
+    digest = hashlib.sha256()
+    for src in _sources():
+        digest.update(os.path.basename(src).encode() + b"\0")
+        with open(src, "rb") as handle:
+            digest.update(handle.read())
+    digest.update(" ".join(NVCC_FLAGS).encode())
+    return digest.hexdigest()
+
+
 def library_is_stale():
+    """True when libhsm_b200.so is missing or was built from other sources.  The comparison is by content
+    (a stamp file written next to the library), so that a copy of the tree with fresh timestamps neither
+    triggers a rebuild nor hides a stale build; without a stamp, modification times decide."""
     if not os.path.exists(LIB_PATH):
         return True
+    if os.path.exists(STAMP_PATH):
+        with open(STAMP_PATH) as handle:
+            return handle.read().strip() != _source_digest()
     built = os.path.getmtime(LIB_PATH)
     return any(os.path.getmtime(src) > built for src in _sources())
 
@@ -85,6 +105,11 @@ def build_library(force=False, verbose=False, jobs=None):
     proc = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, universal_newlines=True)
     if proc.returncode != 0:
         raise RuntimeError("link failed:\n" + proc.stdout)
+    if not os.environ.get("HSM_NVCC_EXTRA"):             # experiment builds are never "the" library
+        with open(STAMP_PATH, "w") as handle:
+            handle.write(_source_digest() + "\n")
+    elif os.path.exists(STAMP_PATH):
+        os.remove(STAMP_PATH)
     return LIB_PATH
 
 
