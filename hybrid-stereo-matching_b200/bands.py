@@ -178,9 +178,15 @@ class RowBandMatcher(object):
             prior_influence_mode="const", n_iter=10):
         p2p = self.exchange == "p2p" and self.world > 1
         with self.engine.stream_context():
+            if p2p:
+                # A neighbour's last iteration of the PREVIOUS call may still be pushing rows into this band's
+                # ghost rows, and its final flag write may still be in flight: every rank drains its own stream,
+                # then all meet, before anybody clears planes or mailboxes for the new call.
+                import torch.distributed as dist
+                self.engine.matcher.synchronize()
+                dist.barrier(group=self.group)
             self.engine.init_fields(image_left, image_right, prior, prior_trust_factor, prior_influence_mode)
             if p2p:
-                import torch.distributed as dist
                 if not self._attached:
                     self._attach_neighbours()
                 self.engine.reset_peers()

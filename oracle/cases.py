@@ -92,6 +92,51 @@ BIG_CASES = [
          calls=[dict(n_iter=15)]),
 ]
 
+# Reference-pinned fixtures for the configurations the CPU oracles cannot re-run inside the test-suite's time
+# budget: generated ONCE by the real reference in the build container (labels + per-plane sha1 / float64 sums),
+# read by the GPU parity tests.  ``cpu`` = which oracles the CPU suite re-checks them with.
+HUGE_CASES = [
+    # BASELINE.json configs[2] (C3) at its real iteration count
+    dict(name="b07_vga_d64_it100", rows=480, cols=640, levels=64, seed=4321, cpu=("c",),
+         calls=[dict(n_iter=100, prior="f64", prior_trust_factor=1.0, prior_influence_mode="adaptive")]),
+    # BASELINE.json configs[4] (C5): 1920x1080, D=256, event prior
+    dict(name="b08_1080p_d256_it1", rows=1080, cols=1920, levels=256, seed=99, cpu=(),
+         calls=[dict(n_iter=1, prior="f64", prior_trust_factor=0.5, prior_influence_mode="const")]),
+    dict(name="b09_1080p_d256_it2", rows=1080, cols=1920, levels=256, seed=99, cpu=(),
+         calls=[dict(n_iter=2, prior="f64", prior_trust_factor=1.0, prior_influence_mode="adaptive")]),
+    # the 32-lane x 2 layout (D 129..256) at a useful size, full and not full
+    dict(name="b10_mid_d256_it5", rows=24, cols=300, levels=256, seed=41, cpu=("c", "numpy"),
+         calls=[dict(n_iter=5, prior="f64", prior_trust_factor=1.0, prior_influence_mode="adaptive")]),
+    dict(name="b11_mid_d200_it4", rows=40, cols=260, levels=200, seed=42, cpu=("c", "numpy"),
+         calls=[dict(n_iter=4, prior="i32", prior_trust_factor=0.5, prior_influence_mode="const")]),
+    # the shipped hybrid configurations at their effective (down-scaled) resolutions, offline call pattern
+    # (experiments/configs/hybrid/*.yaml:19-23, stereo_framebased.py:84-85)
+    dict(name="b12_boxes_80x60_d20", rows=60, cols=80, levels=20, seed=51, cpu=("c", "numpy"),
+         calls=[dict(n_iter=10, prior="f64", prior_trust_factor=1.0, prior_influence_mode="adaptive")]),
+    dict(name="b13_checkerboard_80x60_d22", rows=60, cols=80, levels=22, seed=52, cpu=("c", "numpy"),
+         calls=[dict(n_iter=10, prior="f64", prior_trust_factor=1.0, prior_influence_mode="adaptive")]),
+    dict(name="b14_head_70x60_d27", rows=60, cols=70, levels=27, seed=53, cpu=("c", "numpy"),
+         calls=[dict(n_iter=10, prior="f64", prior_trust_factor=1.0, prior_influence_mode="adaptive")]),
+    dict(name="b15_head_115x120_d50", rows=120, cols=115, levels=50, seed=54, cpu=("c", "numpy"),
+         calls=[dict(n_iter=10, prior="i32", prior_trust_factor=0.5, prior_influence_mode="const")]),
+    # the same disparity counts at DAVIS size (batched bench shapes of DESIGN.md)
+    dict(name="b16_davis_d20_it10", rows=180, cols=240, levels=20, seed=55, cpu=("c",),
+         calls=[dict(n_iter=10, prior="f64", prior_trust_factor=1.0, prior_influence_mode="adaptive")]),
+    dict(name="b17_davis_d50_it10", rows=180, cols=240, levels=50, seed=56, cpu=("c",),
+         calls=[dict(n_iter=10, prior="f64", prior_trust_factor=1.0, prior_influence_mode="adaptive")]),
+    dict(name="b18_davis_d40_it6", rows=180, cols=240, levels=40, seed=57, cpu=("c",),
+         calls=[dict(n_iter=6)]),
+    dict(name="b19_davis_d100_it6", rows=90, cols=240, levels=100, seed=58, cpu=("c",),
+         calls=[dict(n_iter=6, prior="f64", prior_trust_factor=0.5, prior_influence_mode="const")]),
+]
+
+
+def find_case(name):
+    for case in SMALL_CASES + BIG_CASES + HUGE_CASES:
+        if case["name"] == name:
+            return case
+    raise KeyError(name)
+
 
 def tsukuba_rgb():
     data = np.load(os.path.join(GOLDEN_DIR, "tsukuba_rgb.npz"))

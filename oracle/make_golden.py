@@ -42,12 +42,18 @@ def _inputs_sha1(case):
     return digest.hexdigest()
 
 
-def main():
+def main(argv=None):
+    """``python -m oracle.make_golden [case name ...]``: all cases, or only the named ones."""
+    names = list(sys.argv[1:] if argv is None else argv)
     os.makedirs(C.GOLDEN_DIR, exist_ok=True)
-    print("tsukuba ->", _export_tsukuba())
+    if not names:
+        print("tsukuba ->", _export_tsukuba())
     reference = reference_class()
     factory = lambda dim, levels: reference(tuple(dim), levels)
-    for case, small in [(c, True) for c in C.SMALL_CASES] + [(c, False) for c in C.BIG_CASES]:
+    todo = [(c, True) for c in C.SMALL_CASES] + [(c, False) for c in C.BIG_CASES + C.HUGE_CASES]
+    for case, small in todo:
+        if names and case["name"] not in names:
+            continue
         labels, planes = C.run_case(factory, case)
         meta = dict(name=case["name"], inputs_sha1=_inputs_sha1(case), small=small,
                     plane_sha1={k: C.plane_sha1(v) for k, v in planes.items()},
@@ -61,7 +67,7 @@ def main():
             for k, v in planes.items():
                 arrays["plane_" + k] = v
         np.savez_compressed(C.fixture_path(case), **arrays)
-        print("%-34s labels sha1 %s" % (case["name"], meta["labels_sha1"]))
+        print("%-34s labels sha1 %s" % (case["name"], meta["labels_sha1"]), flush=True)
     return 0
 
 

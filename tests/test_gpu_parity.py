@@ -11,7 +11,10 @@ from oracle import mrf_c
 
 pytestmark = pytest.mark.gpu
 
-ALL = [(c, True) for c in C.SMALL_CASES] + [(c, False) for c in C.BIG_CASES]
+# HUGE_CASES: reference-pinned fixtures without stored planes (sha1 only); the two 1080p ones have their own,
+# memory-aware test in test_gpu_full_sizes.py
+ALL = [(c, True) for c in C.SMALL_CASES] + [(c, False) for c in C.BIG_CASES] + \
+      [(c, False) for c in C.HUGE_CASES if c["rows"] < 1000]
 IDS = [c["name"] for c, _ in ALL]
 # (algorithm, data_term): TMA-fed fused kernel with recomputed data term (default) / with the data plane,
 # LDG-fed fused kernel (both), one kernel per direction

@@ -36,6 +36,30 @@ def test_c_oracle_matches_reference_fixture(case, small):
     _check_against_fixture(lambda dim, levels: mrf_c.OracleMRFC(tuple(dim), levels), case, small)
 
 
+HUGE_NUMPY = [c for c in C.HUGE_CASES if "numpy" in c["cpu"]]
+HUGE_C = [c for c in C.HUGE_CASES if "c" in c["cpu"]]
+
+
+@pytest.mark.parametrize("case", HUGE_NUMPY, ids=[c["name"] for c in HUGE_NUMPY])
+def test_numpy_oracle_matches_reference_fixture_huge(case):
+    _check_against_fixture(lambda dim, levels: mrf_numpy.OracleMRF(tuple(dim), levels), case, False)
+
+
+@pytest.mark.parametrize("case", HUGE_C, ids=[c["name"] for c in HUGE_C])
+def test_c_oracle_matches_reference_fixture_huge(case):
+    """Includes C3 at its real 100 iterations (b07).  The 1080p D=256 fixtures (b08, b09) are checked by the
+    GPU tests only: one CPU pass needs ~20 GB and minutes."""
+    _check_against_fixture(lambda dim, levels: mrf_c.OracleMRFC(tuple(dim), levels), case, False)
+
+
+def test_every_huge_fixture_exists_and_names_its_inputs():
+    for case in C.HUGE_CASES:
+        data, meta = C.load_fixture(case)
+        assert meta["name"] == case["name"] and len(meta["inputs_sha1"]) == 40
+        assert data["labels"].shape == (case["rows"], case["cols"])
+        assert set(meta["plane_sha1"]) == {"south", "west", "north", "east", "data"}
+
+
 def test_known_answer_sha1_from_survey():
     """KAT-A / KAT-B label hashes recorded independently in SURVEY.md section 8c."""
     _, meta_a = C.load_fixture(C.BIG_CASES[0])
