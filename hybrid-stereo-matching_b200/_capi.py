@@ -158,6 +158,7 @@ def lib():
         "hsm_selftest_division": ([vp, vp, sz, ctypes.POINTER(ctypes.c_uint64)], ci),
         "hsm_host_alloc": ([sz, ctypes.POINTER(vp)], ci),
         "hsm_host_free": ([vp], ci),
+        "hsm_host_is_pinned": ([vp, ctypes.POINTER(ci)], ci),
     }
     for name, (argtypes, restype) in sig.items():
         fn = getattr(handle, name)

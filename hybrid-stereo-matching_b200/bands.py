@@ -175,7 +175,9 @@ class RowBandMatcher(object):
         eng.unpack(self._recv_up if has_up else None, self._recv_down if has_down else None)
 
     def lbp(self, image_left, image_right, prior=None, prior_trust_factor=0.5,
-            prior_influence_mode="const", n_iter=10):
+            prior_influence_mode="const", n_iter=10, _events=None):
+        """``_events``: optional (begin, end) torch CUDA events recorded on the engine's stream around the
+        iteration loop including its exchanges (bench.py times the loop with them)."""
         p2p = self.exchange == "p2p" and self.world > 1
         with self.engine.stream_context():
             if p2p:
@@ -191,16 +193,20 @@ class RowBandMatcher(object):
                     self._attach_neighbours()
                 self.engine.reset_peers()
                 dist.barrier(group=self.group)          # every mailbox is zero before anyone iterates
+            if _events is not None:
+                _events[0].record(self.engine.stream)
             if p2p or self.world == 1:
                 # no host work between iterations: the whole loop is queued by one native call
                 if int(n_iter) > 0:
                     self.engine.iterate(finalize=True, n_iter=n_iter)
-                return self.engine.labels()
-            for iteration in range(int(n_iter)):
-                last = iteration == int(n_iter) - 1
-                self.engine.iterate(finalize=last)
-                if not last:
-                    self._exchange()
+            else:
+                for iteration in range(int(n_iter)):
+                    last = iteration == int(n_iter) - 1
+                    self.engine.iterate(finalize=last)
+                    if not last:
+                        self._exchange()
+            if _events is not None:
+                _events[1].record(self.engine.stream)
             return self.engine.labels()
 
     def gather(self, local_labels):

@@ -14,6 +14,24 @@ using namespace hsm;
 
 namespace {
 thread_local std::string g_error;
+
+// Every entry point that touches CUDA runs on the matcher's device and puts the caller's current device back
+// when it returns (a caller that drives several GPUs from one thread must not find its device changed).
+struct DeviceScope {
+    int prev = -1, dev;
+    // `active` = false: no CUDA call at all (entry points that may run before the first compute call, i.e.
+    // possibly in the parent of a fork()ed worker)
+    explicit DeviceScope(int device, bool active = true) : dev(device)
+    {
+        if (!active) return;
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) cudaSetDevice(dev);
+    }
+    ~DeviceScope()
+    {
+        if (prev >= 0 && prev != dev) cudaSetDevice(prev);
+    }
+};
 }
 
 namespace hsm {
@@ -99,9 +117,8 @@ size_t arena_layout(hsm_matcher *m, bool assign)
     return off;
 }
 
-int ensure_ready(hsm_matcher *m)
+int ensure_ready(hsm_matcher *m)          // (the caller's DeviceScope has selected m->device)
 {
-    CUDA_TRY(cudaSetDevice(m->device));
     if (m->ready) return HSM_OK;
     if (m->stream == nullptr) {
         CUDA_TRY(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
@@ -139,7 +156,7 @@ int pixel_grid(const hsm_matcher *m, int lpp)
     const size_t groups = 256 / lpp;
     const size_t n_pix = (size_t)m->frames * m->H * m->W;
     size_t blocks = (n_pix + groups - 1) / groups;
-    return (int)std::min<size_t>(blocks, (size_t)148 * 64);
+    return (int)std::min<size_t>(blocks, (size_t)m->sm_count * 64);
 }
 
 }  // namespace
@@ -209,7 +226,7 @@ int load_image(hsm_matcher *m, float *dst, const void *src, int dtype, int slot,
         HSM_TRY(copy_in(m, m->stage[slot], src, n * 8, 0));
         dev_src = m->stage[slot];
     }
-    const int blocks = (int)std::min<size_t>((n + 255) / 256, (size_t)148 * 16);
+    const int blocks = (int)std::min<size_t>((n + 255) / 256, (size_t)m->sm_count * 16);
     k_to_f32<double><<<blocks, 256, 0, m->stream>>>((const double *)dev_src, dst, n, m->W, m->Wp);
     return check_launch(m, "k_to_f32");
 }
@@ -221,7 +238,7 @@ int load_prior(hsm_matcher *m, const void *src, int dtype, size_t n, int on_devi
         HSM_TRY(copy_in(m, m->stage[2], src, n * dtype_size(dtype), 0));
         dev_src = m->stage[2];
     }
-    const int blocks = (int)std::min<size_t>((n + 255) / 256, (size_t)148 * 16);
+    const int blocks = (int)std::min<size_t>((n + 255) / 256, (size_t)m->sm_count * 16);
     const int W = m->W, Wp = m->Wp;
     switch (dtype) {
         case HSM_F32: k_prior_labels<float><<<blocks, 256, 0, m->stream>>>((const float *)dev_src, m->P, n, m->D, W, Wp); break;
@@ -249,9 +266,9 @@ int choose_band_rows(const hsm_matcher *m, int strips, int ctas_per_sm)
     // small frame: latency-, not bandwidth-bound) they may shrink to 4 rows.
     const long per_band = (long)strips * m->frames;
     int min_rows = 12;
-    while (min_rows > 4 && per_band * ((rows + min_rows - 1) / min_rows) < 148L * 3) min_rows -= 2;
+    while (min_rows > 4 && per_band * ((rows + min_rows - 1) / min_rows) < (long)m->sm_count * 3) min_rows -= 2;
     const bool grouped = m->launch_frames < m->frames;
-    const long target = 148L * std::max(1, ctas_per_sm) * (grouped ? 4 : 6);
+    const long target = (long)m->sm_count * std::max(1, ctas_per_sm) * (grouped ? 4 : 6);
     long bands = std::max((target + per_band - 1) / per_band, (long)(rows + 63) / 64);
     bands = std::max(1L, std::min<long>(bands, std::max(1, rows / min_rows)));
     return (int)((rows + bands - 1) / bands);
@@ -520,6 +537,10 @@ int hsm_create(int rows, int cols, int n_levels, int capacity, int device, hsm_m
     LaneCfg cfg;
     if (!lane_cfg(n_levels, &cfg)) return fail(HSM_ERR_ARG, "n_levels %d > 512 is not supported", n_levels);
     if (capacity > 65535) return fail(HSM_ERR_ARG, "capacity %d > 65535", capacity);
+    // element offsets inside one frame are 32-bit in the kernels (row offsets, peer ghost rows)
+    if ((unsigned long long)rows * cols * ((n_levels + 3) / 4 * 4) >= (1ull << 32))
+        return fail(HSM_ERR_ARG, "rows x cols x n_levels = %d x %d x %d needs >= 2^32 elements per plane", rows, cols,
+                    n_levels);
     hsm_matcher *m = new hsm_matcher();
     m->H = rows; m->W = cols; m->Wp = (cols + 3) / 4 * 4; m->D = n_levels; m->Dp = (n_levels + 3) / 4 * 4;
     m->cap = capacity; m->device = device; m->cfg = cfg;
@@ -533,7 +554,7 @@ int hsm_destroy(hsm_matcher *m)
 {
     if (!m) return HSM_OK;
     if (m->ready) {
-        cudaSetDevice(m->device);
+        DeviceScope scope(m->device);
         cudaStreamSynchronize(m->stream);
         for (int side = 0; side < 2; ++side)
             if (m->peer[side].attached && m->peer[side].ipc_base) cudaIpcCloseMemHandle(m->peer[side].ipc_base);
@@ -553,8 +574,8 @@ int hsm_destroy(hsm_matcher *m)
 int hsm_set_stream(hsm_matcher *m, void *cuda_stream)
 {
     if (!m) return fail(HSM_ERR_ARG, "null matcher");
+    DeviceScope scope(m->device, m->ready);
     if (m->ready && m->own_stream) {
-        CUDA_TRY(cudaSetDevice(m->device));
         CUDA_TRY(cudaStreamSynchronize(m->stream));
         CUDA_TRY(cudaStreamDestroy(m->stream));
     }
@@ -627,6 +648,10 @@ int hsm_get_option(hsm_matcher *m, int key, int *value)
 int hsm_device_bytes(int rows, int cols, int n_levels, int capacity, size_t *bytes)
 {
     if (!bytes) return fail(HSM_ERR_ARG, "null bytes");
+    if (rows < 1 || cols < 1 || n_levels < 1 || capacity < 1 || n_levels > 512 || capacity > 65535 ||
+        (unsigned long long)rows * cols * ((n_levels + 3) / 4 * 4) >= (1ull << 32))
+        return fail(HSM_ERR_ARG, "hsm_device_bytes: geometry %d x %d x %d x %d is not supported", rows, cols, n_levels,
+                    capacity);
     hsm_matcher tmp;
     tmp.H = rows; tmp.W = cols; tmp.Wp = (cols + 3) / 4 * 4; tmp.D = n_levels; tmp.Dp = (n_levels + 3) / 4 * 4;
     tmp.cap = capacity;
@@ -644,6 +669,7 @@ int init_fields_impl(hsm_matcher *m, int n_frames, const void *left, const void 
                      int reinit_messages, int on_device, bool release_host)
 {
     if (!m) return fail(HSM_ERR_ARG, "null matcher");
+    DeviceScope scope(m->device);
     if (!left || !right) return fail(HSM_ERR_ARG, "null image pointer");
     if (n_frames < 1 || n_frames > m->cap)
         return fail(HSM_ERR_ARG, "n_frames %d outside [1, capacity %d]", n_frames, m->cap);
@@ -657,13 +683,15 @@ int init_fields_impl(hsm_matcher *m, int n_frames, const void *left, const void 
     HSM_TRY(ensure_ready(m));
     const size_t n = (size_t)n_frames * m->H * m->W;
     m->frames = n_frames;
-    HSM_TRY(load_image(m, m->L, left, image_dtype, 0, n, on_device));
-    HSM_TRY(load_image(m, m->R, right, image_dtype, 1, n, on_device));
+    // on_device: 0 = host arrays, 1 = everything on the device, else bit 0 = images, bit 1 = prior on the device
+    const int images_dev = (on_device & 1), prior_dev = (on_device == 1 || (on_device & 2)) ? 1 : 0;
+    HSM_TRY(load_image(m, m->L, left, image_dtype, 0, n, images_dev));
+    HSM_TRY(load_image(m, m->R, right, image_dtype, 1, n, images_dev));
     m->have_prior = (prior != nullptr && prior_mode != HSM_PRIOR_NONE);
     m->blend.mode = m->have_prior ? prior_mode : kPriorNone;
     m->blend.keep32 = keep_f32;
     m->blend.keep64 = keep_f64;
-    if (m->have_prior) HSM_TRY(load_prior(m, prior, prior_dtype, n, on_device));
+    if (m->have_prior) HSM_TRY(load_prior(m, prior, prior_dtype, n, prior_dev));
     if (reinit_messages) {                                   // mrf.py:43-48
         const size_t bytes = (size_t)n_frames * m->H * m->W * m->Dp * sizeof(float);
         CUDA_TRY(cudaMemsetAsync(m->S, 0, bytes, m->stream));
@@ -675,7 +703,7 @@ int init_fields_impl(hsm_matcher *m, int n_frames, const void *left, const void 
     m->have_fields = true;
     m->dt_valid = false;
     // a host buffer may be reused by the caller as soon as we return
-    if (!on_device && release_host) CUDA_TRY(cudaStreamSynchronize(m->stream));
+    if (on_device != 1 && release_host) CUDA_TRY(cudaStreamSynchronize(m->stream));
     return HSM_OK;
 }
 }  // namespace
@@ -693,6 +721,7 @@ int hsm_init_fields(hsm_matcher *m, int n_frames, const void *left, const void *
 int hsm_iterate(hsm_matcher *m, int n_iter, int finalize)
 {
     if (!m) return fail(HSM_ERR_ARG, "null matcher");
+    DeviceScope scope(m->device);
     if (n_iter < 0) return fail(HSM_ERR_ARG, "n_iter %d < 0", n_iter);
     if (!m->have_fields) return fail(HSM_ERR_STATE, "hsm_iterate before hsm_init_fields");
     if (n_iter == 0) return HSM_OK;
@@ -809,6 +838,7 @@ int hsm_iterate(hsm_matcher *m, int n_iter, int finalize)
 int hsm_readout(hsm_matcher *m, int64_t *labels, int on_device, int async)
 {
     if (!m) return fail(HSM_ERR_ARG, "null matcher");
+    DeviceScope scope(m->device);
     if (!labels) return fail(HSM_ERR_ARG, "null labels pointer");
     if (m->frames == 0) return fail(HSM_ERR_STATE, "hsm_readout before hsm_init_fields");
     if (!m->s_valid) return fail(HSM_ERR_STATE, "south plane is stale: last hsm_iterate was not finalized");
@@ -845,17 +875,18 @@ int hsm_lbp(hsm_matcher *m, int n_frames, const void *left, const void *right, i
 {
     // one queue of work, one synchronisation (in the readout, unless async): with an asynchronous readout the
     // host buffers must stay valid until hsm_sync, so only then are they released here
+    // async == 2: the caller keeps ALL host buffers valid until hsm_sync -- nothing waits here at all
     HSM_TRY(init_fields_impl(m, n_frames, left, right, image_dtype, prior, prior_dtype, prior_mode, keep_f32, keep_f64,
-                             1, on_device, async != 0));
+                             1, on_device, async == 1));
     HSM_TRY(hsm_iterate(m, n_iter, 1));
-    return hsm_readout(m, labels, on_device, async);
+    return hsm_readout(m, labels, on_device & 1, async);
 }
 
 int hsm_sync(hsm_matcher *m)
 {
     if (!m) return fail(HSM_ERR_ARG, "null matcher");
+    DeviceScope scope(m->device, m->ready);
     if (!m->ready) return HSM_OK;
-    CUDA_TRY(cudaSetDevice(m->device));
     CUDA_TRY(cudaStreamSynchronize(m->stream));
     return HSM_OK;
 }
@@ -863,6 +894,7 @@ int hsm_sync(hsm_matcher *m)
 int hsm_get_plane(hsm_matcher *m, int frame, int which, float *out)
 {
     HSM_TRY(check_frame(m, frame, which, 5));
+    DeviceScope scope(m->device);
     if (!out) return fail(HSM_ERR_ARG, "null output");
     HSM_TRY(ensure_ready(m));
     if (which == 0 && !m->s_valid) return fail(HSM_ERR_STATE, "south plane is stale: last hsm_iterate was not finalized");
@@ -877,6 +909,7 @@ int hsm_get_plane(hsm_matcher *m, int frame, int which, float *out)
 int hsm_set_plane(hsm_matcher *m, int frame, int which, const float *in)
 {
     HSM_TRY(check_frame(m, frame, which, 4));
+    DeviceScope scope(m->device);
     if (!in) return fail(HSM_ERR_ARG, "null input");
     HSM_TRY(ensure_ready(m));
     float *dst = plane_ptr(m, which) + (size_t)frame * m->H * m->W * m->Dp;
@@ -890,6 +923,7 @@ int hsm_set_plane(hsm_matcher *m, int frame, int which, const float *in)
 int hsm_get_energy(hsm_matcher *m, int frame, float *out)
 {
     HSM_TRY(check_frame(m, frame, 0, 1));
+    DeviceScope scope(m->device);
     if (!out) return fail(HSM_ERR_ARG, "null output");
     if (m->frames == 0) return fail(HSM_ERR_STATE, "hsm_get_energy before hsm_init_fields");
     if (!m->s_valid) return fail(HSM_ERR_STATE, "south plane is stale: last hsm_iterate was not finalized");
@@ -920,6 +954,7 @@ int hsm_get_energy(hsm_matcher *m, int frame, float *out)
 int hsm_peer_export(hsm_matcher *m, hsm_peer_info *out)
 {
     if (!m || !out) return fail(HSM_ERR_ARG, "null argument");
+    DeviceScope scope(m->device);
     if (m->cap != 1) return fail(HSM_ERR_ARG, "row-band mode needs capacity 1");
     HSM_TRY(ensure_ready(m));
     memset(out, 0, sizeof *out);
@@ -943,6 +978,7 @@ int hsm_peer_export(hsm_matcher *m, hsm_peer_info *out)
 int hsm_peer_attach(hsm_matcher *m, int side, const hsm_peer_info *peer, int same_process)
 {
     if (!m || !peer) return fail(HSM_ERR_ARG, "null argument");
+    DeviceScope scope(m->device);
     if (side != 0 && side != 1) return fail(HSM_ERR_ARG, "side must be 0 (above) or 1 (below)");
     if (m->cap != 1) return fail(HSM_ERR_ARG, "row-band mode needs capacity 1");
     if (peer->cols != m->W || peer->dp != m->Dp) return fail(HSM_ERR_ARG, "neighbour has a different row geometry");
@@ -979,6 +1015,7 @@ int hsm_peer_attach(hsm_matcher *m, int side, const hsm_peer_info *peer, int sam
 int hsm_peer_reset(hsm_matcher *m)
 {
     if (!m) return fail(HSM_ERR_ARG, "null matcher");
+    DeviceScope scope(m->device);
     HSM_TRY(ensure_ready(m));
     CUDA_TRY(cudaMemsetAsync(m->mailbox, 0, hsm_matcher::kMailboxWords * sizeof(unsigned), m->stream));
     CUDA_TRY(cudaStreamSynchronize(m->stream));
@@ -989,10 +1026,10 @@ int hsm_peer_reset(hsm_matcher *m)
 int hsm_peer_detach(hsm_matcher *m)
 {
     if (!m) return fail(HSM_ERR_ARG, "null matcher");
+    DeviceScope scope(m->device, m->ready);
     for (int side = 0; side < 2; ++side) {
         hsm_matcher::Peer &p = m->peer[side];
         if (p.attached && p.ipc_base) {
-            CUDA_TRY(cudaSetDevice(m->device));
             CUDA_TRY(cudaStreamSynchronize(m->stream));
             CUDA_TRY(cudaIpcCloseMemHandle(p.ipc_base));
         }
@@ -1011,6 +1048,7 @@ int hsm_halo_floats(hsm_matcher *m, size_t *count)
 int hsm_halo_pack(hsm_matcher *m, float *top, float *bottom)
 {
     if (!m) return fail(HSM_ERR_ARG, "null matcher");
+    DeviceScope scope(m->device);
     if (m->cap != 1) return fail(HSM_ERR_ARG, "row-band mode needs capacity 1");
     HSM_TRY(ensure_ready(m));
     const size_t row = (size_t)m->W * m->Dp;
@@ -1029,6 +1067,7 @@ int hsm_halo_pack(hsm_matcher *m, float *top, float *bottom)
 int hsm_halo_unpack(hsm_matcher *m, const float *from_above, const float *from_below)
 {
     if (!m) return fail(HSM_ERR_ARG, "null matcher");
+    DeviceScope scope(m->device);
     if (m->cap != 1) return fail(HSM_ERR_ARG, "row-band mode needs capacity 1");
     if (from_above && m->olo < 1) return fail(HSM_ERR_ARG, "no ghost row above row %d", m->olo);
     if (from_below && m->ohi + 1 >= m->H) return fail(HSM_ERR_ARG, "no ghost row below row %d", m->ohi);
@@ -1049,10 +1088,8 @@ int hsm_halo_unpack(hsm_matcher *m, const float *from_above, const float *from_b
 int hsm_get_stats(hsm_matcher *m, hsm_stats *out)
 {
     if (!m || !out) return fail(HSM_ERR_ARG, "null argument");
-    if (m->ready) {
-        CUDA_TRY(cudaSetDevice(m->device));
-        HSM_TRY(resolve_events(m));
-    }
+    DeviceScope scope(m->device, m->ready);
+    if (m->ready) HSM_TRY(resolve_events(m));
     *out = m->stats;
     return HSM_OK;
 }
@@ -1060,10 +1097,8 @@ int hsm_get_stats(hsm_matcher *m, hsm_stats *out)
 int hsm_reset_stats(hsm_matcher *m)
 {
     if (!m) return fail(HSM_ERR_ARG, "null matcher");
-    if (m->ready) {
-        CUDA_TRY(cudaSetDevice(m->device));
-        HSM_TRY(resolve_events(m));
-    }
+    DeviceScope scope(m->device, m->ready);
+    if (m->ready) HSM_TRY(resolve_events(m));
     const uint64_t bytes = m->stats.device_bytes;
     m->stats = hsm_stats{};
     m->stats.device_bytes = bytes;
@@ -1147,6 +1182,20 @@ int hsm_host_alloc(size_t bytes, void **out)
 {
     if (!out) return fail(HSM_ERR_ARG, "null output");
     CUDA_TRY(cudaHostAlloc(out, bytes, cudaHostAllocDefault));
+    return HSM_OK;
+}
+
+int hsm_host_is_pinned(const void *p, int *pinned)
+{
+    if (!pinned) return fail(HSM_ERR_ARG, "null output");
+    cudaPointerAttributes attr;
+    const cudaError_t err = cudaPointerGetAttributes(&attr, p);
+    if (err != cudaSuccess) {                    // (older drivers report unregistered memory as an error)
+        cudaGetLastError();
+        *pinned = 0;
+        return HSM_OK;
+    }
+    *pinned = (attr.type == cudaMemoryTypeHost) ? 1 : 0;
     return HSM_OK;
 }
 

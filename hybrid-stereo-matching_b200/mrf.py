@@ -57,6 +57,14 @@ def pinned_empty(shape, dtype):
     return np.frombuffer(buffer, dtype=dtype, count=count).reshape(shape)
 
 
+def is_pinned(array):
+    """True when the array's memory is page-locked and known to CUDA (``pinned_empty``, a pinned torch tensor,
+    ``cudaHostRegister``): asynchronous copies from pageable memory block the calling thread instead."""
+    flag = ctypes.c_int(0)
+    _capi.check(_capi.lib().hsm_host_is_pinned(array.ctypes.data_as(ctypes.c_void_p), ctypes.byref(flag)))
+    return bool(flag.value)
+
+
 _CAI_CODES = {"<f4": _capi.F32, "<f8": _capi.F64, "<i4": _capi.I32, "<i8": _capi.I64}
 
 
@@ -233,23 +241,44 @@ class StereoMRF(object):
             lanes.append(helper)
         return [self] + lanes[:count - 1]
 
+    def _staging(self, name, shape, dtype):
+        """A page-locked staging array of this lane, grown on demand and reused across calls."""
+        ring = self.__dict__.setdefault("_stage_ring", {})
+        need = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        block = ring.get(name)
+        if block is None or block.nbytes < need:
+            block = ring[name] = pinned_empty((max(need, 1),), np.uint8)
+        return block[:need].view(dtype).reshape(shape)
+
     def lbp_batch(self, images_left, images_right, priors=None, prior_trust_factor=0.5,
                   prior_influence_mode="const", n_iter=10, out=None, lanes=2):
         """``lbp`` over a stack of independent frame pairs ``(N, H, W)`` -> ``(N, H, W)`` int64.
 
-        Frames are processed ``capacity`` at a time, alternating between ``lanes`` matchers
-        so that transfers overlap compute (fully so when the arrays are page-locked, see
-        ``pinned_empty``).  Each frame's result equals what ``lbp`` returns for it alone
-        (every call re-initialises the messages, mrf.py:165).
+        Frames are processed ``capacity`` at a time, alternating between ``lanes`` matchers (own stream, own
+        device buffers) so that transfers overlap compute.  Page-locked arrays (``pinned_empty``) are handed
+        to the copy engine as they are.  Ordinary (pageable) numpy arrays -- what the reference's callers
+        pass (stereo_framebased.py:83-85) -- go through a ring of page-locked staging buffers owned by the
+        lanes: a small thread pool fills the next chunk's staging (float64 images are cast to float32 on the
+        way, exactly ``astype('float32')`` of mrf.py:41-42) while the GPU works on the previous chunk, and
+        labels come back through staging the same way, so the caller never blocks inside a copy.  Each
+        frame's result equals what ``lbp`` returns for it alone (every call re-initialises the messages,
+        mrf.py:165).
         """
         images_left, images_right = np.asarray(images_left), np.asarray(images_right)
-        priors = None if priors is None else np.asarray(priors)
+        device_priors = priors is not None and hasattr(priors, "device_pointer")
+        if priors is not None and not device_priors:
+            priors = np.asarray(priors)
         assert images_left.ndim == 3 and images_left.shape == images_right.shape
         n_total = images_left.shape[0]
         if out is None:
             out = np.empty((n_total, self._rows, self._cols), dtype=np.int64)
         assert out.shape == (n_total, self._rows, self._cols) and out.dtype == np.int64 \
             and out.flags["C_CONTIGUOUS"]
+        if n_total == 0:
+            return out
+        self._check_pair(images_left[:1], images_right[:1], None, True)
+        if priors is not None:
+            assert tuple(priors.shape) == images_right.shape                      # mrf.py:53
         # Chunk size: the capacity, but at least two chunks per lane when there is more than one capacity's
         # worth of frames -- the first chunk's upload and the last chunk's download are the only transfers
         # that cannot overlap compute, so they should be a small part of the call.
@@ -259,18 +288,81 @@ class StereoMRF(object):
             chunk = min(self.capacity, max(-(-n_total // (2 * lanes)), 8))
         chunks = [(start, min(start + chunk, n_total)) for start in range(0, n_total, chunk)]
         workers = self._lanes(max(1, min(lanes, len(chunks))))
+        mode, keep32, keep64 = _blend(priors, prior_trust_factor, prior_influence_mode)
+        lib = _capi.lib()
+
+        def host_input(lane, name, array, image):
+            """(pointer, dtype code, keep-alive) of one chunk input as the C ABI should see it."""
+            if image and array.dtype not in _IMAGE_CODES:
+                array = array.astype("float32")
+            if not image and array.dtype not in _PRIOR_CODES:
+                array = array.astype(np.float64 if array.dtype.kind == "f" else np.int64)
+            if array.flags["C_CONTIGUOUS"] and is_pinned(array):
+                return array, None
+            target_dtype = np.float32 if image else array.dtype
+            staged = lane._staging(name, array.shape, target_dtype)
+            return staged, array                       # (to be filled from `array` by the copy pool)
+
+        pool = self.__dict__.get("_copy_pool")
+        if pool is None:
+            from concurrent.futures import ThreadPoolExecutor
+            pool = self._copy_pool = ThreadPoolExecutor(max_workers=4)
+
+        def fill(pairs):
+            jobs = []
+            for staged, source in pairs:
+                if source is None:
+                    continue
+                # split big copies so that the pool's threads share them (numpy releases the GIL in copyto)
+                parts = max(1, min(4, staged.shape[0]))
+                bounds = np.linspace(0, staged.shape[0], parts + 1).astype(int)
+                for a, b in zip(bounds[:-1], bounds[1:]):
+                    if b > a:
+                        jobs.append(pool.submit(np.copyto, staged[a:b], source[a:b], "same_kind"))
+            for job in jobs:
+                job.result()
+
+        out_pinned = is_pinned(out)
+        pending = {}                                   # lane index -> (staged labels, destination slice)
+
+        def drain(index):
+            entry = pending.pop(index, None)
+            if entry is not None:
+                fill([(entry[1], entry[0])])
+
         for index, (start, stop) in enumerate(chunks):
-            lane = workers[index % len(workers)]
+            which = index % len(workers)
+            lane = workers[which]
+            lane.synchronize()                         # the lane's previous chunk (and its staging) is done
+            drain(which)
+            left, left_src = host_input(lane, "left", images_left[start:stop], True)
+            right, right_src = host_input(lane, "right", images_right[start:stop], True)
+            pairs = [(left, left_src), (right, right_src)]
+            if left.dtype != right.dtype:              # mixed image dtypes: both through float32 staging
+                left, right = left.astype("float32"), right.astype("float32")
+                pairs = []
+            prior_ptr, prior_code, on_device = None, _capi.F32, 0
+            prior = None
+            if device_priors:
+                prior_ptr, prior_code, on_device = ctypes.c_void_p(priors.device_pointer(start)), _capi.I32, 2
+            elif priors is not None:
+                prior, prior_src = host_input(lane, "prior", priors[start:stop], False)
+                pairs.append((prior, prior_src))
+                prior_ptr, prior_code = prior.ctypes.data_as(ctypes.c_void_p), _PRIOR_CODES[prior.dtype]
+            fill(pairs)
+            target = out[start:stop] if out_pinned else lane._staging("labels", (stop - start, self._rows, self._cols),
+                                                                      np.int64)
+            _capi.check(lib.hsm_lbp(lane._handle, stop - start, left.ctypes.data_as(ctypes.c_void_p),
+                                    right.ctypes.data_as(ctypes.c_void_p), _IMAGE_CODES[left.dtype], prior_ptr,
+                                    prior_code, mode, keep32, keep64, int(n_iter),
+                                    target.ctypes.data_as(ctypes.c_void_p), on_device, 2))
+            lane._frames, lane._batched = stop - start, True
+            if not out_pinned:
+                pending[which] = (target, out[start:stop])
+        for which, lane in enumerate(workers):
             lane.synchronize()
-            lane._init_fields(images_left[start:stop], images_right[start:stop],
-                              None if priors is None else priors[start:stop],
-                              prior_trust_factor, prior_influence_mode, True, _batched=True)
-            _capi.check(_capi.lib().hsm_iterate(lane._handle, int(n_iter), 1))
-            target = out[start:stop]
-            _capi.check(_capi.lib().hsm_readout(lane._handle, target.ctypes.data_as(ctypes.c_void_p), 0, 1))
-        for lane in workers:
-            lane.synchronize()
-        self._belief_field_cache = out[chunks[-1][0]:chunks[-1][1]] if chunks else out
+            drain(which)
+        self._belief_field_cache = out[chunks[-1][0]:chunks[-1][1]]
         return out
 
     def lbp_batch_device(self, images_left, images_right, priors, out, prior_trust_factor=0.5,

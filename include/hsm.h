@@ -114,7 +114,8 @@ int hsm_device_bytes(int rows, int cols, int n_levels, int capacity, size_t *byt
  * left/right: n_frames x rows x cols of image_dtype (HSM_F32 / HSM_F64).
  * prior: NULL or n_frames x rows x cols of prior_dtype (any HSM_* type); an entry
  * matches level l iff it equals l exactly (mrf.py:57); -1 / NaN match nothing.
- * on_device != 0: the pointers are device pointers on the matcher's device.
+ * on_device: 0 = host arrays; 1 = all pointers are device pointers on the matcher's device;
+ * 2 = images on the host, prior on the device (a prior rasterised by hsm_rasterise_events_device).
  * The inputs are snapshotted (the online prior is a live shared buffer,
  * online_processing.py:121).
  */
@@ -138,7 +139,9 @@ int hsm_iterate(hsm_matcher *m, int n_iter, int finalize);
  */
 int hsm_readout(hsm_matcher *m, int64_t *labels, int on_device, int async);
 
-/* Replaces StereoMRF.lbp (mrf.py:146-167): init (reinit) + n_iter iterations + readout. */
+/* Replaces StereoMRF.lbp (mrf.py:146-167): init (reinit) + n_iter iterations + readout.
+ * async: 0 = returns when the labels are in `labels`; 1 = returns when the INPUT host buffers may be reused,
+ * labels arrive by hsm_sync; 2 = nothing is waited for: every host buffer stays untouched until hsm_sync. */
 int hsm_lbp(hsm_matcher *m, int n_frames, const void *left, const void *right, int image_dtype,
             const void *prior, int prior_dtype, int prior_mode, float keep_f32, double keep_f64,
             int n_iter, int64_t *labels, int on_device, int async);
@@ -221,6 +224,8 @@ int hsm_selftest_division(const float *a4, const float *b, size_t n, unsigned lo
 /* Pinned host memory for asynchronous transfers. */
 int hsm_host_alloc(size_t bytes, void **out);
 int hsm_host_free(void *p);
+/* *pinned = 1 when `p` lies in page-locked memory known to CUDA (asynchronous copies really are asynchronous) */
+int hsm_host_is_pinned(const void *p, int *pinned);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,70 @@
+"""Inputs of the façade / prior-rasterisation fixtures (``tests/golden/f*.npz``, ``tests/golden/r*.npz``).
+
+TEST INFRASTRUCTURE ONLY.  Shared by ``oracle/make_golden_facade.py`` (which runs the REAL reference classes
+and functions in the build container) and by the tests that replay the same inputs through the product.
+"""
+import os
+
+import numpy as np
+
+from .cases import GOLDEN_DIR
+
+# FramebasedStereoMatching.run (stereo_framebased.py:60-101): sequences at the shipped configurations' scale
+FACADE_CASES = [
+    dict(name="f01_run_priors_per_frame", n=5, rows=14, cols=20, levels=6, seed=50, priors="same"),
+    dict(name="f02_run_more_priors_than_frames", n=5, rows=14, cols=20, levels=6, seed=60, priors="more"),
+    dict(name="f03_run_without_priors", n=4, rows=14, cols=20, levels=6, seed=70, priors=None),
+    dict(name="f04_run_checkerboard_scale", n=6, rows=60, cols=80, levels=22, seed=80, priors="same"),
+    dict(name="f05_run_one_frame_online", n=3, rows=60, cols=70, levels=27, seed=90, priors="online"),
+]
+
+# generate_frames_from_spikes with pivots (hybrid_stereo.py:169-176) and without
+RASTER_CASES = [
+    dict(name="r01_pivots_small", seed=1, n=400, res=(20, 14), t_max=500, interval=100,
+         pivots=[50.0, 100.0, 150.0, 400.0]),
+    dict(name="r02_pivots_overlapping_windows", seed=2, n=3000, res=(80, 60), t_max=1000, interval=250,
+         pivots=list(np.arange(50.0, 1000.0, 50.0))),
+    dict(name="r03_time_intervals", seed=3, n=50, res=(9, 7), t_max=300, interval=100, pivots=None),
+    dict(name="r04_dense_one_frame", seed=5, n=2000, res=(16, 12), t_max=100, interval=100, pivots=[100.0]),
+    dict(name="r05_checkerboard_scale", seed=6, n=20000, res=(80, 60), t_max=2000, interval=50,
+         pivots=list(np.arange(50.0, 2001.0, 50.0)), levels=22, unique_times=True),
+    dict(name="r06_start_time_and_unsorted_pivots", seed=7, n=1500, res=(40, 30), t_max=800, interval=120,
+         pivots=[600.0, 200.0, 410.5, 799.0], start_time=150, unique_times=True),
+]
+
+
+def facade_inputs(case):
+    """(lefts, rights, timestamps, prior_info or None) of a façade case."""
+    import importlib
+    synth = importlib.import_module("hybrid-stereo-matching_b200.synth")
+    n, rows, cols, levels = case["n"], case["rows"], case["cols"], case["levels"]
+    lefts, rights, priors = synth.synthetic_sequence(n, rows, cols, levels, base_seed=case["seed"])
+    ts = np.arange(n) * 50.0 + 50.0
+    kind = case["priors"]
+    if kind is None:
+        return lefts, rights, ts, None
+    if kind == "same":
+        return lefts, rights, ts, {"ts": ts, "priors": priors}
+    if kind == "online":                       # int32 prior with -1 fill (online_processing.py:63,121)
+        return lefts, rights, ts, {"ts": ts, "priors": priors.astype(np.int32)}
+    many_ts = np.arange(12) * 25.0             # more priors than frames: the first one at or after each frame
+    many = np.stack([np.roll(priors[i % n], i, axis=1) for i in range(12)])
+    return lefts, rights, ts, {"ts": many_ts, "priors": many}
+
+
+def raster_events(case):
+    """(xs, ys, ts, zs) of a rasterisation case; the SNN output is not time-ordered."""
+    rng = np.random.default_rng(case["seed"])
+    n, (cols, rows) = case["n"], case["res"]
+    xs, ys = rng.integers(0, cols, n), rng.integers(0, rows, n)
+    if case.get("unique_times"):               # no two events share a timestamp: the result does not depend on
+        ts = np.sort(rng.random(n) * case["t_max"])                      # the sort's handling of ties
+    else:
+        ts = np.sort(rng.integers(0, case["t_max"], n)).astype(np.float64)
+    perm = rng.permutation(n)
+    zs = rng.integers(0, case.get("levels", 20), n).astype(np.float64)
+    return xs[perm], ys[perm], ts[perm], zs[perm]
+
+
+def fixture_path(case):
+    return os.path.join(GOLDEN_DIR, case["name"] + ".npz")

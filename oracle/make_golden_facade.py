@@ -1,0 +1,43 @@
+"""Generate ``tests/golden/f*.npz`` / ``r*.npz`` by running the REAL reference callers either side of the
+hot path in this container: ``FramebasedStereoMatching`` (oracle/facade_ref.py) and
+``generate_frames_from_spikes`` (oracle/frames_ref.py).  TEST INFRASTRUCTURE ONLY; run once from the repo
+root (``python -m oracle.make_golden_facade``), outputs are committed."""
+import sys
+
+import numpy as np
+
+from . import facade_cases as F
+from . import facade_ref, frames_ref
+
+
+def main():
+    facade_class = facade_ref.load()
+    for case in F.FACADE_CASES:
+        lefts, rights, ts, info = F.facade_inputs(case)
+        facade = facade_class((case["cols"], case["rows"]), case["levels"],
+                              inputs={"left": lefts, "right": rights, "ts": ts})
+        if case["priors"] == "online":         # the online call pattern: run_one_frame(left, right, prior, n_iter=k)
+            for i in range(case["n"]):
+                facade.run_one_frame(lefts[i], rights[i], info["priors"][i], n_iter=3 + i)
+        else:
+            facade.run(info)
+        out = facade.get_output()
+        np.savez_compressed(F.fixture_path(case), depth=out.astype(np.int8), timestamps=facade.get_timestamps(),
+                            dtype=np.asarray(str(out.dtype)))
+        print("%-36s %s %s" % (case["name"], out.shape, out.dtype), flush=True)
+    _, rasterise = frames_ref.load()
+    for case in F.RASTER_CASES:
+        xs, ys, ts, zs = F.raster_events(case)
+        arrays = {}
+        for fill in (-1, "nan"):
+            frames, stamps = rasterise(case["res"], xs, ys, ts, zs, start_time=case.get("start_time", 0),
+                                       time_interval=case["interval"], pivots=case["pivots"], non_pixel_value=fill)
+            arrays["frames_%s" % fill] = frames
+            arrays["stamps_%s" % fill] = np.asarray(stamps)
+        np.savez_compressed(F.fixture_path(case), **arrays)
+        print("%-36s %s" % (case["name"], arrays["frames_-1"].shape), flush=True)
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
