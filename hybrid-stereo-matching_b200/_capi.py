@@ -153,7 +153,12 @@ def lib():
         "hsm_peer_detach": ([vp], ci),
         "hsm_get_stats": ([vp, ctypes.POINTER(Stats)], ci),
         "hsm_reset_stats": ([vp], ci),
-        "hsm_rasterise_events": ([sz, vp, vp, vp, vp, ci, ci, ci, cd, vp, ci], ci),
+        "hsm_rasterise_events": ([sz, vp, vp, vp, vp, ci, vp, vp, ci, ci, ci, cd, vp, vp, ci], ci),
+        "hsm_rescale_frames": ([ci, ci, ci, vp, ci, ci, vp, ci], ci),
+        "hsm_adjust_priors": ([ci, ci, ci, vp, cd, ci, vp, ci], ci),
+        "hsm_device_alloc": ([sz, ci, ctypes.POINTER(vp)], ci),
+        "hsm_device_free": ([vp, ci], ci),
+        "hsm_device_read": ([vp, vp, sz, ci], ci),
         "hsm_normalise_contrast": ([ci, ci, ci, vp, vp, ci], ci),
         "hsm_selftest_division": ([vp, vp, sz, ctypes.POINTER(ctypes.c_uint64)], ci),
         "hsm_host_alloc": ([sz, ctypes.POINTER(vp)], ci),

@@ -68,8 +68,14 @@ size_t dtype_size(int dtype)
 // defaults per disparity range; 6..8 trade lanes per pixel for float4s per lane (fewer
 // shuffle steps and per-pixel operations per element, more registers per thread).
 const LaneCfg kLaneTable[] = {{4, 1, 256}, {8, 1, 256}, {16, 1, 512}, {32, 1, 512}, {32, 2, 512},
-                              {32, 4, 256}, {4, 2, 256}, {8, 2, 256}, {16, 2, 512}};
-constexpr int kLaneTableSize = 9;
+                              {32, 4, 256}, {4, 2, 256}, {8, 2, 256}, {16, 2, 512},
+                              // entries 10..13: lanes-per-pixel counts that are not a power of two (default
+                              // kernel family only): the reference's shipped disparity counts 20 and 22 are 5 and 6
+                              // float4 chunks per pixel
+                              {5, 1, 256}, {6, 1, 256}, {5, 2, 256}, {6, 2, 256}};
+constexpr int kLaneTableSize = 13;
+
+bool is_pow2(int v) { return (v & (v - 1)) == 0; }
 
 bool lane_cfg_fits(const LaneCfg &c, int D) { return D <= 4 * c.lpp * c.vpl; }
 
@@ -85,6 +91,17 @@ bool lane_cfg(int D, LaneCfg *c)
     else return false;
     *c = kLaneTable[pick];
     return true;
+}
+
+// Lane layout of the default kernel family: the power-of-two choice unless 5 or 6 chunk slots per lane group
+// waste fewer lanes (D = 17..24 and 33..48; for 25..32 and 49..64 the 8-lane layouts are already as good).
+LaneCfg lane_cfg_st(int D, const LaneCfg &base)
+{
+    if (D > 16 && D <= 20) return kLaneTable[9];
+    if (D > 20 && D <= 24) return kLaneTable[10];
+    if (D > 32 && D <= 40) return kLaneTable[11];
+    if (D > 40 && D <= 48) return kLaneTable[12];
+    return base;
 }
 
 size_t plane_floats(const hsm_matcher *m) { return (size_t)m->cap * m->H * m->W * m->Dp; }
@@ -190,6 +207,19 @@ int ensure_data_plane(hsm_matcher *m)
     });
     HSM_TRY(check_launch(m, "k_cost_volume"));
     m->dt_valid = true;
+    return HSM_OK;
+}
+
+// Real zeros in memory for the four message planes of the current batch, if they are only logically zero.
+int materialise_zero_messages(hsm_matcher *m)
+{
+    if (!m->zero_messages) return HSM_OK;
+    const size_t bytes = (size_t)std::max(m->frames, 1) * m->H * m->W * m->Dp * sizeof(float);
+    CUDA_TRY(cudaMemsetAsync(m->S, 0, bytes, m->stream));
+    CUDA_TRY(cudaMemsetAsync(m->Wm[m->cur], 0, bytes, m->stream));
+    CUDA_TRY(cudaMemsetAsync(m->Nm[m->cur], 0, bytes, m->stream));
+    CUDA_TRY(cudaMemsetAsync(m->Em[m->cur], 0, bytes, m->stream));
+    m->zero_messages = false;
     return HSM_OK;
 }
 
@@ -370,6 +400,7 @@ IterArgs iter_args(hsm_matcher *m, int strips, bool store_s, int ctas_per_sm)
     a.store_s = store_s ? 1 : 0;
     a.has_prior = m->have_prior ? 1 : 0;
     a.frame0 = m->launch_frame0;
+    a.zero_in = m->zero_messages ? 1 : 0;
     for (int side = 0; side < 2; ++side) {
         const hsm_matcher::Peer &p = m->peer[side];
         a.pushW[side] = p.attached ? p.Wm[m->cur ^ 1] : nullptr;
@@ -407,6 +438,24 @@ int ensure_maps(hsm_matcher *m)
     HSM_TRY(make_image_map(m, &m->tmI.L, m->L, false, px + 4));
     HSM_TRY(make_image_map(m, &m->tmI.R, m->R, false, rbox));
     HSM_TRY(make_image_map(m, &m->tmI.P, m->P, true, px + 4));
+    // the default kernel family's own set (the same boxes unless its lane layout differs)
+    {
+        const int px5 = (m->cfg5.nt / 32) * (32 / m->cfg5.lpp);
+        for (int i = 0; i < 2; ++i) {
+            HSM_TRY(make_plane_map(m, &m->st.tmW[i], m->Wm[i], px5));
+            HSM_TRY(make_plane_map(m, &m->st.tmN[i], m->Nm[i], px5));
+            HSM_TRY(make_plane_map(m, &m->st.tmE[i], m->Em[i], px5));
+            HSM_TRY(make_plane_map(m, &m->st.tsW[i], m->Wm[i], px5 - 2));
+            HSM_TRY(make_plane_map(m, &m->st.tsN[i], m->Nm[i], px5 - 2));
+            HSM_TRY(make_plane_map(m, &m->st.tsE[i], m->Em[i], px5 - 2));
+        }
+        HSM_TRY(make_plane_map(m, &m->st.tmD, m->Dt, px5));
+        const int dcov5 = 4 * m->cfg5.lpp * m->cfg5.vpl, rseg5 = px5 + dcov5 + 4;
+        const int rbox5 = rseg5 <= 256 ? rseg5 : ((rseg5 / 2 + 31) / 32 * 32);
+        HSM_TRY(make_image_map(m, &m->st.tmI.L, m->L, false, px5 + 4));
+        HSM_TRY(make_image_map(m, &m->st.tmI.R, m->R, false, rbox5));
+        HSM_TRY(make_image_map(m, &m->st.tmI.P, m->P, true, px5 + 4));
+    }
     m->maps_valid = true;
     return HSM_OK;
 }
@@ -543,7 +592,7 @@ int hsm_create(int rows, int cols, int n_levels, int capacity, int device, hsm_m
                     n_levels);
     hsm_matcher *m = new hsm_matcher();
     m->H = rows; m->W = cols; m->Wp = (cols + 3) / 4 * 4; m->D = n_levels; m->Dp = (n_levels + 3) / 4 * 4;
-    m->cap = capacity; m->device = device; m->cfg = cfg;
+    m->cap = capacity; m->device = device; m->cfg = cfg; m->cfg5 = lane_cfg_st(n_levels, cfg);
     m->vlo = 0; m->vhi = rows - 1; m->olo = 0; m->ohi = rows - 1;
     m->frames = 0;
     *out = m;
@@ -614,7 +663,10 @@ int hsm_set_option(hsm_matcher *m, int key, int value)
             LaneCfg c;
             if (value == 0) lane_cfg(m->D, &c); else c = kLaneTable[value - 1];
             if (!lane_cfg_fits(c, m->D)) return fail(HSM_ERR_ARG, "lane config %d covers fewer than %d levels", value, m->D);
-            m->cfg = c; m->lane_config = value; m->maps_valid = false;
+            // 0: defaults for both families; a power-of-two entry: both families; 10..13: default family only
+            if (is_pow2(c.lpp)) { m->cfg = c; m->cfg5 = value == 0 ? lane_cfg_st(m->D, c) : c; }
+            else m->cfg5 = c;
+            m->lane_config = value; m->maps_valid = false;
             return HSM_OK;
         }
         case HSM_OPT_STAGES:
@@ -692,12 +744,8 @@ int init_fields_impl(hsm_matcher *m, int n_frames, const void *left, const void 
     m->blend.keep32 = keep_f32;
     m->blend.keep64 = keep_f64;
     if (m->have_prior) HSM_TRY(load_prior(m, prior, prior_dtype, n, prior_dev));
-    if (reinit_messages) {                                   // mrf.py:43-48
-        const size_t bytes = (size_t)n_frames * m->H * m->W * m->Dp * sizeof(float);
-        CUDA_TRY(cudaMemsetAsync(m->S, 0, bytes, m->stream));
-        CUDA_TRY(cudaMemsetAsync(m->Wm[m->cur], 0, bytes, m->stream));
-        CUDA_TRY(cudaMemsetAsync(m->Nm[m->cur], 0, bytes, m->stream));
-        CUDA_TRY(cudaMemsetAsync(m->Em[m->cur], 0, bytes, m->stream));
+    if (reinit_messages) {                                   // mrf.py:43-48: logically zero, see matcher.hpp
+        m->zero_messages = true;
         m->s_valid = true;
     }
     m->have_fields = true;
@@ -727,6 +775,9 @@ int hsm_iterate(hsm_matcher *m, int n_iter, int finalize)
     if (n_iter == 0) return HSM_OK;
     HSM_TRY(ensure_ready(m));
     if (m->algorithm == 0 || m->data_term == 0) HSM_TRY(ensure_data_plane(m));
+    // only the TMA-fed kernels can take "all messages are zero" as an out-of-tensor load
+    if (!((m->algorithm == 2 || m->algorithm == 5 || m->algorithm == 6) && tma_supported(m)))
+        HSM_TRY(materialise_zero_messages(m));
     std::pair<cudaEvent_t, cudaEvent_t> ev;
     if (m->pending.size() >= 512) HSM_TRY(resolve_events(m));
     if (!m->pool.empty()) { ev = m->pool.back(); m->pool.pop_back(); }
@@ -757,6 +808,7 @@ int hsm_iterate(hsm_matcher *m, int n_iter, int finalize)
             m->pending.push_back(ev);
             m->stats.iterations += (uint64_t)n_iter;
             m->s_valid = finalize != 0;
+            m->zero_messages = false;
             return HSM_OK;
         }
     }
@@ -822,6 +874,7 @@ int hsm_iterate(hsm_matcher *m, int n_iter, int finalize)
         else
             HSM_TRY(launch_fused_any(m, store_s));
       }
+      m->zero_messages = false;            // (every group of the first iteration has been queued)
     }
     m->launch_frame0 = 0; m->launch_frames = m->frames; m->launch_stream = m->stream;
     if (grouped) {
@@ -843,6 +896,7 @@ int hsm_readout(hsm_matcher *m, int64_t *labels, int on_device, int async)
     if (m->frames == 0) return fail(HSM_ERR_STATE, "hsm_readout before hsm_init_fields");
     if (!m->s_valid) return fail(HSM_ERR_STATE, "south plane is stale: last hsm_iterate was not finalized");
     HSM_TRY(ensure_ready(m));
+    HSM_TRY(materialise_zero_messages(m));
     const Geo g = geometry(m);
     const bool dt_load = m->dt_valid || !m->have_fields;
     if (dt_load) HSM_TRY(ensure_data_plane(m));
@@ -898,6 +952,7 @@ int hsm_get_plane(hsm_matcher *m, int frame, int which, float *out)
     if (!out) return fail(HSM_ERR_ARG, "null output");
     HSM_TRY(ensure_ready(m));
     if (which == 0 && !m->s_valid) return fail(HSM_ERR_STATE, "south plane is stale: last hsm_iterate was not finalized");
+    HSM_TRY(materialise_zero_messages(m));
     if (which == 4) HSM_TRY(ensure_data_plane(m));
     const float *src = plane_ptr(m, which) + (size_t)frame * m->H * m->W * m->Dp;
     CUDA_TRY(cudaMemcpy2DAsync(out, (size_t)m->D * 4, src, (size_t)m->Dp * 4, (size_t)m->D * 4,
@@ -912,6 +967,8 @@ int hsm_set_plane(hsm_matcher *m, int frame, int which, const float *in)
     DeviceScope scope(m->device);
     if (!in) return fail(HSM_ERR_ARG, "null input");
     HSM_TRY(ensure_ready(m));
+    if (m->frames <= frame) m->frames = frame + 1;
+    HSM_TRY(materialise_zero_messages(m));
     float *dst = plane_ptr(m, which) + (size_t)frame * m->H * m->W * m->Dp;
     CUDA_TRY(cudaMemcpy2DAsync(dst, (size_t)m->Dp * 4, in, (size_t)m->D * 4, (size_t)m->D * 4,
                                (size_t)m->H * m->W, cudaMemcpyHostToDevice, m->stream));
@@ -928,6 +985,7 @@ int hsm_get_energy(hsm_matcher *m, int frame, float *out)
     if (m->frames == 0) return fail(HSM_ERR_STATE, "hsm_get_energy before hsm_init_fields");
     if (!m->s_valid) return fail(HSM_ERR_STATE, "south plane is stale: last hsm_iterate was not finalized");
     HSM_TRY(ensure_ready(m));
+    HSM_TRY(materialise_zero_messages(m));
     HSM_TRY(ensure_data_plane(m));
     // stream-ordered scratch for the energy planes of the current batch
     float *scratch = nullptr;
@@ -1051,6 +1109,7 @@ int hsm_halo_pack(hsm_matcher *m, float *top, float *bottom)
     DeviceScope scope(m->device);
     if (m->cap != 1) return fail(HSM_ERR_ARG, "row-band mode needs capacity 1");
     HSM_TRY(ensure_ready(m));
+    HSM_TRY(materialise_zero_messages(m));
     const size_t row = (size_t)m->W * m->Dp;
     const float *planes[3] = {m->Wm[m->cur], m->Nm[m->cur], m->Em[m->cur]};
     for (int i = 0; i < 3; ++i) {
@@ -1072,6 +1131,7 @@ int hsm_halo_unpack(hsm_matcher *m, const float *from_above, const float *from_b
     if (from_above && m->olo < 1) return fail(HSM_ERR_ARG, "no ghost row above row %d", m->olo);
     if (from_below && m->ohi + 1 >= m->H) return fail(HSM_ERR_ARG, "no ghost row below row %d", m->ohi);
     HSM_TRY(ensure_ready(m));
+    HSM_TRY(materialise_zero_messages(m));
     const size_t row = (size_t)m->W * m->Dp;
     float *planes[3] = {m->Wm[m->cur], m->Nm[m->cur], m->Em[m->cur]};
     for (int i = 0; i < 3; ++i) {
@@ -1105,38 +1165,91 @@ int hsm_reset_stats(hsm_matcher *m)
     return HSM_OK;
 }
 
-int hsm_rasterise_events(size_t n_events, const int *x, const int *y, const double *z, const int *frame,
-                         int n_frames, int rows, int cols, double fill, double *out, int device)
+namespace {
+// device memory and a stream that are released on every return path
+struct Scratch {
+    std::vector<void *> blocks;
+    cudaStream_t stream = nullptr;
+    ~Scratch()
+    {
+        if (stream) cudaStreamSynchronize(stream);
+        for (void *p : blocks) cudaFree(p);
+        if (stream) cudaStreamDestroy(stream);
+    }
+    int alloc(void **out, size_t bytes)
+    {
+        *out = nullptr;
+        CUDA_TRY(cudaMalloc(out, std::max<size_t>(bytes, 16)));
+        blocks.push_back(*out);
+        return HSM_OK;
+    }
+};
+int device_sm_count(int device)
+{
+    int count = 148;
+    cudaDeviceGetAttribute(&count, cudaDevAttrMultiProcessorCount, device);
+    return count;
+}
+}  // namespace
+
+int hsm_rasterise_events(size_t n_events, const int32_t *x, const int32_t *y, const double *t, const double *z,
+                         int n_frames, const double *lo, const double *hi, int hi_inclusive, int rows, int cols,
+                         double fill, double *frames_out, int32_t *labels_device, int device)
 {
     if (n_frames < 0 || rows < 1 || cols < 1) return fail(HSM_ERR_ARG, "bad raster geometry");
-    if (!out || (n_events && (!x || !y || !z || !frame))) return fail(HSM_ERR_ARG, "null argument");
+    if ((!frames_out && !labels_device) || (n_events && (!x || !y || !t || !z)) || (n_frames && (!lo || !hi)))
+        return fail(HSM_ERR_ARG, "null argument");
     const size_t n_pixels = (size_t)n_frames * rows * cols;
     if (n_pixels == 0) return HSM_OK;
-    if (n_events > 0x7fffffffull) return fail(HSM_ERR_ARG, "too many events");
-    CUDA_TRY(cudaSetDevice(device));
-    int *dx = nullptr, *dy = nullptr, *df = nullptr, *dw = nullptr;
-    double *dz = nullptr, *dout = nullptr;
-    CUDA_TRY(cudaMalloc((void **)&dw, n_pixels * sizeof(int)));
-    CUDA_TRY(cudaMalloc((void **)&dout, n_pixels * sizeof(double)));
-    CUDA_TRY(cudaMemset(dw, 0xff, n_pixels * sizeof(int)));          // -1: no event
+    if (n_events >= 0xffffffffull) return fail(HSM_ERR_ARG, "too many events");
+    DeviceScope scope(device);
+    Scratch s;
+    CUDA_TRY(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    bool monotone = true;
+    for (int f = 1; f < n_frames; ++f) monotone = monotone && lo[f] >= lo[f - 1] && hi[f] >= hi[f - 1];
+    int *dx = nullptr, *dy = nullptr, *derr = nullptr;
+    double *dt = nullptr, *dz = nullptr, *dlo = nullptr, *dhi = nullptr, *dframes = nullptr;
+    unsigned long long *latest = nullptr;
+    unsigned *winner = nullptr;
+    HSM_TRY(s.alloc((void **)&latest, n_pixels * sizeof(unsigned long long)));
+    HSM_TRY(s.alloc((void **)&winner, n_pixels * sizeof(unsigned)));
+    HSM_TRY(s.alloc((void **)&derr, sizeof(int)));
+    HSM_TRY(s.alloc((void **)&dlo, (size_t)n_frames * sizeof(double)));
+    HSM_TRY(s.alloc((void **)&dhi, (size_t)n_frames * sizeof(double)));
+    HSM_TRY(s.alloc((void **)&dx, n_events * sizeof(int)));
+    HSM_TRY(s.alloc((void **)&dy, n_events * sizeof(int)));
+    HSM_TRY(s.alloc((void **)&dt, n_events * sizeof(double)));
+    HSM_TRY(s.alloc((void **)&dz, n_events * sizeof(double)));
+    if (frames_out) HSM_TRY(s.alloc((void **)&dframes, n_pixels * sizeof(double)));
+    CUDA_TRY(cudaMemsetAsync(latest, 0, n_pixels * sizeof(unsigned long long), s.stream));
+    CUDA_TRY(cudaMemsetAsync(winner, 0, n_pixels * sizeof(unsigned), s.stream));
+    CUDA_TRY(cudaMemsetAsync(derr, 0, sizeof(int), s.stream));
+    CUDA_TRY(cudaMemcpyAsync(dlo, lo, (size_t)n_frames * sizeof(double), cudaMemcpyHostToDevice, s.stream));
+    CUDA_TRY(cudaMemcpyAsync(dhi, hi, (size_t)n_frames * sizeof(double), cudaMemcpyHostToDevice, s.stream));
+    const int sms = device_sm_count(device);
     if (n_events) {
-        CUDA_TRY(cudaMalloc((void **)&dx, n_events * sizeof(int)));
-        CUDA_TRY(cudaMalloc((void **)&dy, n_events * sizeof(int)));
-        CUDA_TRY(cudaMalloc((void **)&df, n_events * sizeof(int)));
-        CUDA_TRY(cudaMalloc((void **)&dz, n_events * sizeof(double)));
-        CUDA_TRY(cudaMemcpy(dx, x, n_events * sizeof(int), cudaMemcpyHostToDevice));
-        CUDA_TRY(cudaMemcpy(dy, y, n_events * sizeof(int), cudaMemcpyHostToDevice));
-        CUDA_TRY(cudaMemcpy(df, frame, n_events * sizeof(int), cudaMemcpyHostToDevice));
-        CUDA_TRY(cudaMemcpy(dz, z, n_events * sizeof(double), cudaMemcpyHostToDevice));
-        const int blocks = (int)std::min<size_t>((n_events + 255) / 256, (size_t)148 * 16);
-        k_raster_winner<<<blocks, 256>>>(dx, dy, df, n_events, rows, cols, dw);
+        CUDA_TRY(cudaMemcpyAsync(dx, x, n_events * sizeof(int), cudaMemcpyHostToDevice, s.stream));
+        CUDA_TRY(cudaMemcpyAsync(dy, y, n_events * sizeof(int), cudaMemcpyHostToDevice, s.stream));
+        CUDA_TRY(cudaMemcpyAsync(dt, t, n_events * sizeof(double), cudaMemcpyHostToDevice, s.stream));
+        CUDA_TRY(cudaMemcpyAsync(dz, z, n_events * sizeof(double), cudaMemcpyHostToDevice, s.stream));
+        RasterArgs a;
+        a.x = dx; a.y = dy; a.t = dt; a.n_events = n_events; a.lo = dlo; a.hi = dhi; a.n_frames = n_frames;
+        a.hi_inclusive = hi_inclusive ? 1 : 0; a.monotone = monotone ? 1 : 0; a.rows = rows; a.cols = cols;
+        const int blocks = (int)std::min<size_t>((n_events + 255) / 256, (size_t)sms * 16);
+        k_raster_latest<<<blocks, 256, 0, s.stream>>>(a, latest, derr);
+        CUDA_TRY(cudaGetLastError());
+        k_raster_winner<<<blocks, 256, 0, s.stream>>>(a, latest, winner, derr);
         CUDA_TRY(cudaGetLastError());
     }
-    const int blocks = (int)std::min<size_t>((n_pixels + 255) / 256, (size_t)148 * 16);
-    k_raster_gather<<<blocks, 256>>>(dw, dz, n_pixels, fill, dout);
+    const int blocks = (int)std::min<size_t>((n_pixels + 255) / 256, (size_t)sms * 16);
+    k_raster_emit<<<blocks, 256, 0, s.stream>>>(winner, dz, n_pixels, fill, dframes, (int *)labels_device);
     CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaMemcpy(out, dout, n_pixels * sizeof(double), cudaMemcpyDeviceToHost));
-    cudaFree(dx); cudaFree(dy); cudaFree(df); cudaFree(dz); cudaFree(dw); cudaFree(dout);
+    int error = 0;
+    CUDA_TRY(cudaMemcpyAsync(&error, derr, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+    if (frames_out)
+        CUDA_TRY(cudaMemcpyAsync(frames_out, dframes, n_pixels * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
+    CUDA_TRY(cudaStreamSynchronize(s.stream));
+    if (error) return fail(HSM_ERR_ARG, "event coordinate out of bounds for a %d x %d frame", rows, cols);
     return HSM_OK;
 }
 
@@ -1146,15 +1259,87 @@ int hsm_normalise_contrast(int n_frames, int rows, int cols, const double *in, d
     if (n_frames == 0) return HSM_OK;
     if (!in || !out) return fail(HSM_ERR_ARG, "null argument");
     const size_t frame_elems = (size_t)rows * cols, bytes = (size_t)n_frames * frame_elems * sizeof(double);
-    CUDA_TRY(cudaSetDevice(device));
+    DeviceScope scope(device);
+    Scratch s;
+    CUDA_TRY(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
     double *din = nullptr, *dout = nullptr;
-    CUDA_TRY(cudaMalloc((void **)&din, bytes));
-    CUDA_TRY(cudaMalloc((void **)&dout, bytes));
-    CUDA_TRY(cudaMemcpy(din, in, bytes, cudaMemcpyHostToDevice));
-    k_normalise_contrast<<<n_frames, 1024>>>(din, dout, frame_elems);
+    HSM_TRY(s.alloc((void **)&din, bytes));
+    HSM_TRY(s.alloc((void **)&dout, bytes));
+    CUDA_TRY(cudaMemcpyAsync(din, in, bytes, cudaMemcpyHostToDevice, s.stream));
+    k_normalise_contrast<<<n_frames, 1024, 0, s.stream>>>(din, dout, frame_elems);
     CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaMemcpy(out, dout, bytes, cudaMemcpyDeviceToHost));
-    cudaFree(din); cudaFree(dout);
+    CUDA_TRY(cudaMemcpyAsync(out, dout, bytes, cudaMemcpyDeviceToHost, s.stream));
+    CUDA_TRY(cudaStreamSynchronize(s.stream));
+    return HSM_OK;
+}
+
+int hsm_rescale_frames(int n_frames, int rows, int cols, const double *in, int out_rows, int out_cols, double *out,
+                       int device)
+{
+    if (n_frames < 0 || rows < 1 || cols < 1 || out_rows < 1 || out_cols < 1) return fail(HSM_ERR_ARG, "bad frame geometry");
+    if (n_frames == 0) return HSM_OK;
+    if (!in || !out) return fail(HSM_ERR_ARG, "null argument");
+    const size_t in_bytes = (size_t)n_frames * rows * cols * sizeof(double);
+    const size_t out_bytes = (size_t)n_frames * out_rows * out_cols * sizeof(double);
+    DeviceScope scope(device);
+    Scratch s;
+    CUDA_TRY(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    double *din = nullptr, *dout = nullptr;
+    HSM_TRY(s.alloc((void **)&din, in_bytes));
+    HSM_TRY(s.alloc((void **)&dout, out_bytes));
+    CUDA_TRY(cudaMemcpyAsync(din, in, in_bytes, cudaMemcpyHostToDevice, s.stream));
+    k_rescale_bilinear<<<n_frames, 1024, 0, s.stream>>>(din, dout, rows, cols, out_rows, out_cols);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(out, dout, out_bytes, cudaMemcpyDeviceToHost, s.stream));
+    CUDA_TRY(cudaStreamSynchronize(s.stream));
+    return HSM_OK;
+}
+
+int hsm_adjust_priors(int n_frames, int rows, int cols, const double *prior, double nondata, int time_arrow, float *out,
+                      int device)
+{
+    if (n_frames < 0 || rows < 1 || cols < 1) return fail(HSM_ERR_ARG, "bad frame geometry");
+    if (time_arrow != 1 && time_arrow != -1) return fail(HSM_ERR_ARG, "time_arrow must be +1 or -1");
+    if (n_frames == 0) return HSM_OK;
+    if (!prior || !out) return fail(HSM_ERR_ARG, "null argument");
+    const size_t n = (size_t)n_frames * rows * cols;
+    DeviceScope scope(device);
+    Scratch s;
+    CUDA_TRY(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    double *din = nullptr;
+    float *dout = nullptr;
+    HSM_TRY(s.alloc((void **)&din, n * sizeof(double)));
+    HSM_TRY(s.alloc((void **)&dout, n * sizeof(float)));
+    CUDA_TRY(cudaMemcpyAsync(din, prior, n * sizeof(double), cudaMemcpyHostToDevice, s.stream));
+    const int blocks = (int)std::min<size_t>((n + 255) / 256, (size_t)device_sm_count(device) * 16);
+    k_adjust_priors<<<blocks, 256, 0, s.stream>>>(din, dout, n_frames, rows, cols, nondata, time_arrow);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(out, dout, n * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
+    CUDA_TRY(cudaStreamSynchronize(s.stream));
+    return HSM_OK;
+}
+
+int hsm_device_alloc(size_t bytes, int device, void **out)
+{
+    if (!out) return fail(HSM_ERR_ARG, "null output");
+    DeviceScope scope(device);
+    CUDA_TRY(cudaMalloc(out, std::max<size_t>(bytes, 16)));
+    return HSM_OK;
+}
+
+int hsm_device_free(void *p, int device)
+{
+    if (!p) return HSM_OK;
+    DeviceScope scope(device);
+    CUDA_TRY(cudaFree(p));
+    return HSM_OK;
+}
+
+int hsm_device_read(void *dst_host, const void *src_device, size_t bytes, int device)
+{
+    if (!dst_host || !src_device) return fail(HSM_ERR_ARG, "null argument");
+    DeviceScope scope(device);
+    CUDA_TRY(cudaMemcpy(dst_host, src_device, bytes, cudaMemcpyDeviceToHost));
     return HSM_OK;
 }
 
@@ -1170,7 +1355,7 @@ int hsm_selftest_division(const float *a4, const float *b, size_t n, unsigned lo
     CUDA_TRY(cudaMemcpy(da, a4, n * sizeof(float4), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(db, b, n * sizeof(float), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemset(dm, 0, sizeof(unsigned long long)));
-    k_division_selftest<<<148 * 8, 256>>>(da, db, dm, n);
+    k_division_selftest<<<device_sm_count(0) * 8, 256>>>(da, db, dm, n);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpy(mismatches, dm, sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     cudaFree(da); cudaFree(db); cudaFree(dm);

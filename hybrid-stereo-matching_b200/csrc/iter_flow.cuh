@@ -70,7 +70,8 @@ __global__ void __launch_bounds__(NT, NT == 256 ? (VPL == 1 ? HSM_TMA_MIN_BLOCKS
     unsigned *s_next;
     {
         using SL = StageLayout<LPP, VPL, NT>;
-        constexpr int TX = NT / LPP - 2, SLOTS = NT + 2 * LPP;
+        using PM = PixelMap<LPP, NT>;
+        constexpr int TX = PM::PX - 2, SLOTS = PM::LANES + 2 * LPP;
         const unsigned ost_bytes = (((unsigned)TX * (unsigned)g.Dp * 4u) + 127u) & ~127u;
         unsigned char *after = smem_raw + (size_t)stages * SL::stage_bytes(g.Dp, DT_LOAD) + 6u * ost_bytes +
                                (size_t)2 * VPL * SLOTS * sizeof(float4);
@@ -157,7 +158,8 @@ __global__ void __launch_bounds__(NT, NT == 256 ? (VPL == 1 ? HSM_TMA_MIN_BLOCKS
         tmast_task<LPP, VPL, NT, DT_LOAD, FULL, PUSH, true, 2>(&maps.tmW[in], &maps.tmN[in], &maps.tmE[in], &maps.tmD,
                                                             &maps.tmL, &maps.tmR, &maps.tmP, &maps.tsW[out],
                                                             &maps.tsN[out], &maps.tsE[out], g, a, stages, bx, by, frame,
-                                                            store_s, smem_raw, stage, phase, first, pp, &pending);
+                                                            store_s, smem_raw, stage, phase, first, pp,
+                                                            a.zero_in != 0 && it == 0, &pending);
         first = false;
         pending.local = tile + by * f.strips + bx;
         pending.local_value = (unsigned)it + 1u;

@@ -87,7 +87,7 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 // Byte size of one pipeline stage and where the image segments sit inside it (T24 only).
 template <int LPP, int VPL, int NT>
 struct StageLayout {
-    static constexpr int PX = NT / LPP;
+    static constexpr int PX = PixelMap<LPP, NT>::PX;
     static constexpr int DCOV = 4 * LPP * VPL;
     // The innermost TMA coordinate must be 16-byte aligned, so image segments start at a column
     // that is a multiple of 4 (up to 3 columns early) and are 4 columns longer than needed.
@@ -169,9 +169,10 @@ __global__ void __launch_bounds__(NT, (NT == 256 && VPL == 1) ? HSM_TMA_MIN_BLOC
         unsigned tx = NPL * row_floats * 4u;
         if (!DT_LOAD) tx += SL::LBOX * 4u + SL::NRB * SL::RBOX * 4u + (a.has_prior ? SL::LBOX * 4u : 0u);
         mbar_expect_tx(&full[s], tx);
-        tma_load_4d(dst, &tmW, &full[s], 0, xs0 - 1, yy, frame);
-        tma_load_4d(dst + row_floats, &tmN, &full[s], 0, xs0 - 1, yy, frame);
-        tma_load_4d(dst + 2 * row_floats, &tmE, &full[s], 0, xs0 - 1, yy, frame);
+        const int frame_ld = a.zero_in ? -1 : frame;      // out-of-tensor frame: zero fill, no memory read
+        tma_load_4d(dst, &tmW, &full[s], 0, xs0 - 1, yy, frame_ld);
+        tma_load_4d(dst + row_floats, &tmN, &full[s], 0, xs0 - 1, yy, frame_ld);
+        tma_load_4d(dst + 2 * row_floats, &tmE, &full[s], 0, xs0 - 1, yy, frame_ld);
         if (DT_LOAD) {
             tma_load_4d(dst + 3 * row_floats, &tmD, &full[s], 0, xs0 - 1, yy, frame);
         } else {

@@ -76,19 +76,23 @@ __device__ __forceinline__ void tmast_task(const CUtensorMap *tmW, const CUtenso
                                            const CUtensorMap *tsE, const Geo &g, const IterArgs &a, const int stages,
                                            const int bx, const int by, const int frame, const bool store_s_arg,
                                            unsigned char *smem_raw, int &stage, uint32_t &phase, const bool first_task,
-                                           const PushPtrs &pp, const FlowPending *publish = nullptr)
+                                           const PushPtrs &pp, const bool zero_in,
+                                           const FlowPending *publish = nullptr)
 {
     using SL = StageLayout<LPP, VPL, NT>;
-    constexpr int PX = NT / LPP;
+    using PM = PixelMap<LPP, NT>;
+    constexpr int PX = PM::PX;
     constexpr int TX = PX - 2;
-    constexpr int SLOTS = NT + 2 * LPP;
+    constexpr int SLOTS = PM::LANES + 2 * LPP;   // [0, LANES): real lanes; then a scratch pixel and a zero pixel
     constexpr int NPL = DT_LOAD ? 4 : 3;
     const bool STORE_S = S_MODE == 2 ? store_s_arg : (S_MODE == 1);
 
     const int tid = threadIdx.x;
-    const int px = tid / LPP;
+    PM pm;
+    pm.init(tid);
+    const int px = pm.px;
     Lane<LPP, VPL> ln;
-    ln.init(tid % LPP, g.D, g.Dp);
+    ln.init(pm.c, g.D, g.Dp, pm.seg0);
 
     const unsigned row_floats = (unsigned)PX * (unsigned)g.Dp;          // one plane's row segment
     const unsigned stage_bytes = SL::stage_bytes(g.Dp, DT_LOAD);
@@ -105,6 +109,10 @@ __device__ __forceinline__ void tmast_task(const CUtensorMap *tmW, const CUtenso
 #else
     const int frame_mem = frame;
 #endif
+    // The first iteration after a message reset reads all-zero W, N, E (mrf.py:43-48).  Instead of zeroing the
+    // planes and reading them back, its loads name a frame outside the tensor: the TMA unit fills the stage with
+    // zeros without touching memory.
+    const int frame_ld = zero_in ? -1 : frame_mem;
     const int xs0 = bx * TX;
     const int shift_l = (xs0 - 1) & 3, shift_r = (xs0 - SL::DCOV) & 3;    // see StageLayout
     const int x = xs0 - 1 + px;
@@ -115,13 +123,13 @@ __device__ __forceinline__ void tmast_task(const CUtensorMap *tmW, const CUtenso
     const unsigned row_stride = (unsigned)g.W * (unsigned)g.Dp;
     const int n_rows = yb1 - yb0 + 3;                                    // rows yb0-1 .. yb1+1
 
-    const bool st_w = px >= 2;                                 // W'(y, x-1)  -> staging slot px-2
-    const bool st_n = px >= 1 && px <= PX - 2;                 // N'(y-1, x)  -> staging slot px-1   (and S')
-    const bool st_e = px <= PX - 3;                            // E'(y-1, x+1)-> staging slot px
-    const bool st_s = in_x && px >= 1 && px <= PX - 2;         // S' goes out with plain stores (last iteration only)
-    const int rd_slot = (x < 0) ? (NT + LPP + ln.c) : (tid + LPP);
+    const bool st_w = pm.real && px >= 2;                      // W'(y, x-1)  -> staging slot px-2
+    const bool st_n = pm.real && px >= 1 && px <= PX - 2;      // N'(y-1, x)  -> staging slot px-1   (and S')
+    const bool st_e = pm.real && px <= PX - 3;                 // E'(y-1, x+1)-> staging slot px
+    const bool st_s = in_x && st_n;                            // S' goes out with plain stores (last iteration only)
+    const int rd_slot = (x < 0) ? (PM::LANES + LPP + ln.c) : (pm.slot + LPP);
     // W' exchange slots of this lane as shared-space addresses: [parity][v] are constant offsets from these
-    const unsigned ex_wr_addr = smem_u32(exch) + 16u * (unsigned)tid;
+    const unsigned ex_wr_addr = smem_u32(exch) + 16u * (unsigned)pm.slot;
     unsigned ex_rd_addr = smem_u32(exch) + 16u * (unsigned)rd_slot;
     // keep it in a register: left alone, the compiler re-derives the slot from the thread index in every row
     asm volatile("" : "+r"(ex_rd_addr));
@@ -134,7 +142,7 @@ __device__ __forceinline__ void tmast_task(const CUtensorMap *tmW, const CUtenso
         }
         if (tid < 2 * LPP) {
 #pragma unroll
-            for (int v = 0; v < VPL; ++v) ex(0, v, NT + tid) = ex(1, v, NT + tid) = zero4();
+            for (int v = 0; v < VPL; ++v) ex(0, v, PM::LANES + tid) = ex(1, v, PM::LANES + tid) = zero4();
         }
         __syncthreads();
     }
@@ -147,9 +155,9 @@ __device__ __forceinline__ void tmast_task(const CUtensorMap *tmW, const CUtenso
         unsigned tx = NPL * row_floats * 4u;
         if (!DT_LOAD) tx += SL::LBOX * 4u + SL::NRB * SL::RBOX * 4u + (a.has_prior ? SL::LBOX * 4u : 0u);
         mbar_expect_tx(&full[s], tx);
-        tma_load_4d(dst, tmW, &full[s], 0, xs0 - 1, yy, frame_mem);
-        tma_load_4d(dst + row_floats, tmN, &full[s], 0, xs0 - 1, yy, frame_mem);
-        tma_load_4d(dst + 2 * row_floats, tmE, &full[s], 0, xs0 - 1, yy, frame_mem);
+        tma_load_4d(dst, tmW, &full[s], 0, xs0 - 1, yy, frame_ld);
+        tma_load_4d(dst + row_floats, tmN, &full[s], 0, xs0 - 1, yy, frame_ld);
+        tma_load_4d(dst + 2 * row_floats, tmE, &full[s], 0, xs0 - 1, yy, frame_ld);
         if (DT_LOAD) {
             tma_load_4d(dst + 3 * row_floats, tmD, &full[s], 0, xs0 - 1, yy, frame);
         } else {
@@ -308,7 +316,8 @@ __device__ __forceinline__ void tmast_task(const CUtensorMap *tmW, const CUtenso
             }
         }
 #pragma unroll
-        for (int v = 0; v < VPL; ++v) sts_f4(ex_wr_addr + par * EX_PAR + v * EX_V, t.q[v]);
+        for (int v = 0; v < VPL; ++v)
+            if (PM::POW2 || pm.real) sts_f4(ex_wr_addr + par * EX_PAR + v * EX_V, t.q[v]);
         if (st_w) stage_out(st_wp, par, t);
         if constexpr (PUSH) push_row(pp.W, y, -1, st_w && (x - 1) < g.W && y <= yb1, t);
         if (STORE_S) {                         // block-uniform: the last iteration only
@@ -405,7 +414,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? (VPL == 1 ? HSM_TMA_MIN_BLOCKS
     }
     tmast_task<LPP, VPL, NT, DT_LOAD, FULL, PUSH, false, STORE_S ? 1 : 0>(
         &tmW, &tmN, &tmE, &tmD, &tmL, &tmR, &tmP, &tsW, &tsN, &tsE, g, a, stages, (int)blockIdx.x, (int)blockIdx.y,
-        a.frame0 + (int)blockIdx.z, STORE_S, smem_raw, stage, phase, true, pp);
+        a.frame0 + (int)blockIdx.z, STORE_S, smem_raw, stage, phase, true, pp, a.zero_in != 0);
 }
 
 }  // namespace hsm

@@ -16,7 +16,8 @@ template <int LPP, int VPL, int NT>
 int launch_flow(hsm_matcher *m, int n_iter, bool finalize, bool *launched)
 {
     *launched = false;
-    constexpr int PX = NT / LPP, TX = PX - 2, SLOTS = NT + 2 * LPP;
+    using PM = PixelMap<LPP, NT>;
+    constexpr int TX = PM::PX - 2, SLOTS = PM::LANES + 2 * LPP;
     const bool dt_load = (m->data_term == 0);
     const size_t stage_bytes = StageLayout<LPP, VPL, NT>::stage_bytes(m->Dp, dt_load);
     const size_t ost_bytes = ((size_t)TX * m->Dp * 4 + 127) & ~(size_t)127;
@@ -70,10 +71,10 @@ int launch_flow(hsm_matcher *m, int n_iter, bool finalize, bool *launched)
     }
     FlowMaps maps;
     for (int i = 0; i < 2; ++i) {
-        maps.tmW[i] = m->tmW[i]; maps.tmN[i] = m->tmN[i]; maps.tmE[i] = m->tmE[i];
-        maps.tsW[i] = m->tsW[i]; maps.tsN[i] = m->tsN[i]; maps.tsE[i] = m->tsE[i];
+        maps.tmW[i] = m->st.tmW[i]; maps.tmN[i] = m->st.tmN[i]; maps.tmE[i] = m->st.tmE[i];
+        maps.tsW[i] = m->st.tsW[i]; maps.tsN[i] = m->st.tsN[i]; maps.tsE[i] = m->st.tsE[i];
     }
-    maps.tmD = m->tmD; maps.tmL = m->tmI.L; maps.tmR = m->tmI.R; maps.tmP = m->tmI.P;
+    maps.tmD = m->st.tmD; maps.tmL = m->st.tmI.L; maps.tmR = m->st.tmI.R; maps.tmP = m->st.tmI.P;
     const bool full = (m->D == 4 * LPP * VPL);
 #define HSM_LAUNCH_FLOW(T, F)                                                                                \
     do {                                                                                                     \
@@ -103,7 +104,7 @@ int launch_flow(hsm_matcher *m, int n_iter, bool finalize, bool *launched)
 
 int HSM_FLOW_ENTRY(hsm_matcher *m, int n_iter, bool finalize, bool *launched)
 {
-    HSM_DISPATCH(m->cfg, { return launch_flow<LPP, VPL, NT>(m, n_iter, finalize, launched); });
+    HSM_DISPATCH_ST(m->cfg5, { return launch_flow<LPP, VPL, NT>(m, n_iter, finalize, launched); });
     return fail(HSM_ERR_ARG, "no lane configuration");
 }
 

@@ -16,7 +16,8 @@ template <int LPP, int VPL, int NT>
 int launch_tmast(hsm_matcher *m, bool store_s, bool *launched)
 {
     *launched = false;
-    constexpr int PX = NT / LPP, TX = PX - 2, SLOTS = NT + 2 * LPP;
+    using PM = PixelMap<LPP, NT>;
+    constexpr int TX = PM::PX - 2, SLOTS = PM::LANES + 2 * LPP;
     const bool dt_load = (m->data_term == 0);
     const size_t stage_bytes = StageLayout<LPP, VPL, NT>::stage_bytes(m->Dp, dt_load);
     const size_t ost_bytes = ((size_t)TX * m->Dp * 4 + 127) & ~(size_t)127;
@@ -45,8 +46,9 @@ int launch_tmast(hsm_matcher *m, bool store_s, bool *launched)
         auto kernel = store_s ? k_iter_tmast<LPP, VPL, NT, T, F, HSM_PUSH, true>                             \
                               : k_iter_tmast<LPP, VPL, NT, T, F, HSM_PUSH, false>;                           \
         CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
-        CUDA_TRY(cudaLaunchKernelEx(&cfg, kernel, m->tmW[in], m->tmN[in], m->tmE[in], m->tmD, m->tmI.L, m->tmI.R,   \
-                                    m->tmI.P, m->tsW[out], m->tsN[out], m->tsE[out], g, a, stages));           \
+        CUDA_TRY(cudaLaunchKernelEx(&cfg, kernel, m->st.tmW[in], m->st.tmN[in], m->st.tmE[in], m->st.tmD,           \
+                                    m->st.tmI.L, m->st.tmI.R, m->st.tmI.P, m->st.tsW[out], m->st.tsN[out],        \
+                                    m->st.tsE[out], g, a, stages));                                            \
     } while (0)
     if (full) { if (dt_load) HSM_LAUNCH_TMAST(true, true); else HSM_LAUNCH_TMAST(false, true); }
     else { if (dt_load) HSM_LAUNCH_TMAST(true, false); else HSM_LAUNCH_TMAST(false, false); }
@@ -62,7 +64,7 @@ int launch_tmast(hsm_matcher *m, bool store_s, bool *launched)
 
 int HSM_TMAST_ENTRY(hsm_matcher *m, bool store_s, bool *launched)
 {
-    HSM_DISPATCH(m->cfg, { return launch_tmast<LPP, VPL, NT>(m, store_s, launched); });
+    HSM_DISPATCH_ST(m->cfg5, { return launch_tmast<LPP, VPL, NT>(m, store_s, launched); });
     return fail(HSM_ERR_ARG, "no lane configuration");
 }
 

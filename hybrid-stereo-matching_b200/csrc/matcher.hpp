@@ -64,15 +64,42 @@ struct LaneCfg {
         else HSM_DISPATCH_CASE(16, 2, 512, __VA_ARGS__)         \
     } while (0)
 
+// The default kernel family (k_iter_tmast / k_iter_flow) also has lane layouts whose lanes-per-pixel count is
+// not a power of two (PixelMap in kernels.cuh); the other families and the plane kernels only have the list above.
+#define HSM_DISPATCH_ST(cfg, ...)                               \
+    do {                                                        \
+        const hsm::LaneCfg cfg__ = (cfg);                       \
+        HSM_DISPATCH_CASE(4, 1, 256, __VA_ARGS__)               \
+        else HSM_DISPATCH_CASE(8, 1, 256, __VA_ARGS__)          \
+        else HSM_DISPATCH_CASE(16, 1, 512, __VA_ARGS__)         \
+        else HSM_DISPATCH_CASE(32, 1, 512, __VA_ARGS__)         \
+        else HSM_DISPATCH_CASE(32, 2, 512, __VA_ARGS__)         \
+        else HSM_DISPATCH_CASE(32, 4, 256, __VA_ARGS__)         \
+        else HSM_DISPATCH_CASE(4, 2, 256, __VA_ARGS__)          \
+        else HSM_DISPATCH_CASE(8, 2, 256, __VA_ARGS__)          \
+        else HSM_DISPATCH_CASE(16, 2, 512, __VA_ARGS__)         \
+        else HSM_DISPATCH_CASE(5, 1, 256, __VA_ARGS__)          \
+        else HSM_DISPATCH_CASE(6, 1, 256, __VA_ARGS__)          \
+        else HSM_DISPATCH_CASE(5, 2, 256, __VA_ARGS__)          \
+        else HSM_DISPATCH_CASE(6, 2, 256, __VA_ARGS__)          \
+    } while (0)
+
 struct ImageMaps {
     CUtensorMap L, R, P;
+};
+
+// tensor maps of the default kernel family for its own lane layout (boxes of its PX / TX pixels)
+struct StMaps {
+    CUtensorMap tmW[2], tmN[2], tmE[2], tmD, tsW[2], tsN[2], tsE[2];
+    ImageMaps tmI;
 };
 
 }  // namespace hsm
 
 struct hsm_matcher {
     int H = 0, W = 0, Wp = 0, D = 0, Dp = 0, cap = 0, device = 0;
-    hsm::LaneCfg cfg{};
+    hsm::LaneCfg cfg{};          // lane layout of the plane kernels and the alternative iteration kernels (power of two)
+    hsm::LaneCfg cfg5{};         // lane layout of the default kernel family (may be 5 or 6 lanes per pixel)
     bool ready = false;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
@@ -94,7 +121,12 @@ struct hsm_matcher {
     CUtensorMap tmW[2], tmN[2], tmE[2], tmD;
     CUtensorMap tsW[2], tsN[2], tsE[2];          // store maps (box = TX output pixels)
     hsm::ImageMaps tmI;
+    hsm::StMaps st;
     bool maps_valid = false;
+    // hsm_init_fields(reinit) does not clear the message planes: it records that they are LOGICALLY zero.  The
+    // first iteration then reads no plane at all (zero-filled by the TMA unit), and whoever needs real zeros in
+    // memory (read-backs, the alternative kernels, n_iter = 0) materialises them first.
+    bool zero_messages = false;
     int vlo = 0, vhi = 0, olo = 0, ohi = 0;
     // row-band mode with peer-to-peer halo push (hsm_peer_*): side 0 = band above, 1 = band below
     struct Peer {

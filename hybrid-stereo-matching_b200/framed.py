@@ -22,10 +22,12 @@ def select_priors(prior_info, frame_timestamps):
     pick for each frame the first prior whose timestamp is >= the frame's (np.searchsorted,
     side='left'); otherwise use them in order."""
     n_frames = len(frame_timestamps)
+    priors = prior_info["priors"]
+    on_device = hasattr(priors, "device_pointer")          # priors.DevicePriors: rasterised on the GPU, still there
     if len(prior_info["ts"]) > n_frames:
         indices = [np.searchsorted(prior_info["ts"], t_frame, side="left") for t_frame in frame_timestamps]
-        return np.asarray(prior_info["priors"])[indices]
-    return np.asarray(prior_info["priors"])
+        return np.asarray(priors.download() if on_device else priors)[indices]
+    return priors if on_device else np.asarray(priors)
 
 
 def next_n_iter(n_iter, last_duration_ms, frame_budget_ms, min_iter=1, max_iter=10, adaptive=True):

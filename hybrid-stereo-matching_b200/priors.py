@@ -1,13 +1,20 @@
-"""Event list -> prior frames (the producer of the matcher's ``prior`` input).
+"""Event list -> prior frames (the producer of the matcher's ``prior`` input), on the GPU.
 
 Mirrors ``split_frames_by_time`` and ``generate_frames_from_spikes`` of the reference
 (stereovis/utils/frames_io.py:184-248), which ``hybrid_stereo.py:169-176`` calls with the frame
-timestamps as ``pivots`` and ``non_pixel_value=-1``.  The index bookkeeping stays on the host
-(numpy, same calls as the reference so that tie order matches); the scatter -- last event per pixel
-wins -- runs on the GPU through ``hsm_rasterise_events``.
+timestamps as ``pivots`` and ``non_pixel_value=-1``.  The reference sorts the events by time and lets numpy's
+fancy assignment keep the last one per pixel; here the host only turns ``pivots`` / ``time_interval`` into one
+time window per frame and ``hsm_rasterise_events`` finds the latest event per (frame, pixel) on the device --
+no sort, and with ``rasterise_priors_on_device`` the int32 label frames stay on the GPU and feed
+``StereoMRF.lbp_batch`` / ``FramebasedStereoMatching.run`` directly.
+
+Events with EQUAL timestamps on the same pixel of the same frame: the reference's order among them is whatever
+its (unstable) ``np.argsort`` produces; here the event that comes later in the input arrays wins, which is
+what a stable sort gives.
 """
 import ctypes
 import logging
+import weakref
 
 import numpy as np
 
@@ -16,55 +23,107 @@ from . import _capi
 logger = logging.getLogger(__name__)
 
 
+def _windows(ts, start_time, time_interval, pivots):
+    """Per-frame time windows: (lo, hi, hi_inclusive, timestamps).
+
+    With pivots a frame is [tick - time_interval, tick] (frames_io.py:200-202); without, frames are cut where
+    ``t % time_interval`` wraps around in the time-ordered event stream (frames_io.py:193-198), i.e. frame k
+    is [T_(k-1), T_k) for the wrap-around timestamps T_k, and the events after the last wrap are dropped.
+    Events before ``start_time`` never count (frames_io.py:190-191)."""
+    if pivots is not None:
+        ticks = np.asarray(pivots, dtype=np.float64).reshape(-1)
+        lo = np.maximum(ticks - time_interval, float(start_time))
+        return lo, ticks.copy(), True, pivots
+    times = np.sort(np.asarray(ts, dtype=np.float64))
+    times = times[times >= start_time]
+    phase = times % time_interval
+    wraps = np.flatnonzero(phase[1:] - phase[:-1] < 0) + 1
+    stamps = times[wraps]
+    lo = np.concatenate([[float(start_time)], stamps[:-1]]) if stamps.size else np.zeros(0)
+    return lo, stamps.astype(np.float64), False, stamps
+
+
 def split_frames_by_time(ts, start_time=0, time_interval=100, pivots=None):
-    """Indices of the events of each frame, chronological (frames_io.py:184-204)."""
+    """Indices of the events of each frame, chronological (frames_io.py:184-204): the frames' time windows
+    located by binary search in the time-ordered event list (ties in input order)."""
     ts = np.asarray(ts)
-    sorted_indices = np.argsort(ts)
-    sorted_time = ts[sorted_indices]
-    sorted_time = sorted_time[sorted_time >= start_time]
-    sorted_indices = sorted_indices[sorted_indices.size - sorted_time.size:]
-    if pivots is None:
-        wraps = np.convolve(sorted_time % time_interval, [1, -1], mode="valid") < 0
-        ticks = np.where(np.concatenate([np.array([False]), wraps]))[0]
-        timestamps = sorted_time[ticks]
-        indices_frames = np.split(sorted_indices, ticks)[:-1]      # the last, incomplete frame is dropped
-    else:
-        indices_frames = [sorted_indices[np.where(np.logical_and(sorted_time >= tick - time_interval,
-                                                                 sorted_time <= tick))[0]] for tick in pivots]
-        timestamps = pivots
-    return indices_frames, timestamps
+    lo, hi, inclusive, timestamps = _windows(ts, start_time, time_interval, pivots)
+    order = np.argsort(ts, kind="stable")
+    times = np.asarray(ts, dtype=np.float64)[order]
+    first = np.searchsorted(times, lo, side="left")
+    last = np.searchsorted(times, hi, side="right" if inclusive else "left")
+    return [order[a:max(a, b)] for a, b in zip(first, last)], timestamps
+
+
+class DevicePriors(object):
+    """int32 prior frames ``(N, rows, cols)`` in device memory (``-1`` = no event / matches no level)."""
+
+    def __init__(self, n_frames, rows, cols, device):
+        self.shape, self.device, self.dtype = (int(n_frames), int(rows), int(cols)), int(device), np.dtype(np.int32)
+        pointer = ctypes.c_void_p()
+        _capi.check(_capi.lib().hsm_device_alloc(max(self.nbytes, 1), self.device, ctypes.byref(pointer)))
+        self._address = pointer.value
+        weakref.finalize(self, _capi.lib().hsm_device_free, ctypes.c_void_p(self._address), self.device)
+
+    @property
+    def nbytes(self):
+        return self.shape[0] * self.shape[1] * self.shape[2] * 4
+
+    def __len__(self):
+        return self.shape[0]
+
+    def device_pointer(self, frame=0):
+        return self._address + int(frame) * self.shape[1] * self.shape[2] * 4
+
+    def download(self):
+        out = np.empty(self.shape, dtype=np.int32)
+        if out.size:
+            _capi.check(_capi.lib().hsm_device_read(out.ctypes.data_as(ctypes.c_void_p), ctypes.c_void_p(self._address),
+                                                    out.nbytes, self.device))
+        return out
+
+
+def _rasterise(resolution, xs, ys, ts, zs, start_time, time_interval, pivots, fill, want_host, want_device, device):
+    xs = np.ascontiguousarray(np.asarray(xs).astype(int), dtype=np.int32)
+    ys = np.ascontiguousarray(np.asarray(ys).astype(int), dtype=np.int32)
+    ts64 = np.ascontiguousarray(np.asarray(ts), dtype=np.float64)
+    zs64 = np.ascontiguousarray(np.asarray(zs), dtype=np.float64)
+    lo, hi, inclusive, timestamps = _windows(ts64, start_time, time_interval, pivots)
+    lo, hi = np.ascontiguousarray(lo, dtype=np.float64), np.ascontiguousarray(hi, dtype=np.float64)
+    n_cols, n_rows = resolution
+    n_frames = int(lo.size)
+    frames = np.empty((n_frames, n_rows, n_cols), dtype=np.float64) if want_host else None
+    labels = DevicePriors(n_frames, n_rows, n_cols, device) if want_device else None
+    ptr = lambda a: None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+    status = _capi.lib().hsm_rasterise_events(
+        xs.size, ptr(xs), ptr(ys), ptr(ts64), ptr(zs64), n_frames, ptr(lo), ptr(hi), 1 if inclusive else 0,
+        int(n_rows), int(n_cols), float(fill), ptr(frames),
+        ctypes.c_void_p(labels.device_pointer()) if labels is not None else None, int(device))
+    if status == _capi.ERR_ARG and b"out of bounds" in _capi.lib().hsm_last_error():
+        raise IndexError(_capi.lib().hsm_last_error().decode())          # numpy's error for such an index
+    _capi.check(status)
+    return frames, labels, timestamps
 
 
 def generate_frames_from_spikes(resolution, xs, ys, ts, zs, start_time=0, time_interval=100, pivots=None,
                                 non_pixel_value="nan", return_time_indices=False, device=0):
-    """Frames ``(N, rows, cols)`` float64 buffered from events (frames_io.py:207-248)."""
+    """Frames ``(N, rows, cols)`` float64 buffered from events (frames_io.py:207-248), as host arrays."""
     logger.info("Generating %s frames from spikes",
                 len(pivots) if pivots is not None else int(np.max(ts) / time_interval))
-    xs, ys = np.asarray(xs).astype(int), np.asarray(ys).astype(int)
-    ts, zs = np.asarray(ts), np.asarray(zs)
-    indices_frames, timestamps = split_frames_by_time(ts, start_time, time_interval, pivots)
-    n_cols, n_rows = resolution
-    fill = float(non_pixel_value)
-    n_frames = len(indices_frames)
-    order = np.concatenate(indices_frames) if n_frames else np.zeros(0, dtype=np.int64)
-    order = order.astype(np.int64)
-    frame_of = np.repeat(np.arange(n_frames, dtype=np.int32), [len(i) for i in indices_frames])
-    ex, ey = xs[order], ys[order]
-    # numpy fancy indexing semantics: negative indices wrap once, anything else is an IndexError
-    for name, values, size in (("1", ey, n_rows), ("2", ex, n_cols)):
-        bad = (values < -size) | (values >= size)
-        if bad.any():
-            raise IndexError("index %d is out of bounds for axis %s with size %d" % (values[bad][0], name, size))
-    ex = np.ascontiguousarray(np.where(ex < 0, ex + n_cols, ex), dtype=np.int32)
-    ey = np.ascontiguousarray(np.where(ey < 0, ey + n_rows, ey), dtype=np.int32)
-    ez = np.ascontiguousarray(zs[order], dtype=np.float64)
-    frames = np.empty((n_frames, n_rows, n_cols), dtype=np.float64)
-    ptr = lambda a: a.ctypes.data_as(ctypes.c_void_p)
-    _capi.check(_capi.lib().hsm_rasterise_events(order.size, ptr(ex), ptr(ey), ptr(ez), ptr(frame_of), n_frames,
-                                                 n_rows, n_cols, fill, ptr(frames), int(device)))
+    frames, _, timestamps = _rasterise(resolution, xs, ys, ts, zs, start_time, time_interval, pivots,
+                                       float(non_pixel_value), True, False, device)
     if return_time_indices:
-        return frames, timestamps, indices_frames
+        return frames, timestamps, split_frames_by_time(ts, start_time, time_interval, pivots)[0]
     return frames, timestamps
+
+
+def rasterise_priors_on_device(resolution, xs, ys, ts, zs, start_time=0, time_interval=100, pivots=None, device=0):
+    """The same frames as ``generate_frames_from_spikes(..., non_pixel_value=-1)`` but as int32 label frames
+    that stay in device memory: ``(DevicePriors, timestamps)``.  Pass the ``DevicePriors`` as ``priors`` to
+    ``StereoMRF.lbp_batch`` or inside ``prior_info`` to ``FramebasedStereoMatching.run``."""
+    _, labels, timestamps = _rasterise(resolution, xs, ys, ts, zs, start_time, time_interval, pivots, -1.0, False,
+                                       True, device)
+    return labels, timestamps
 
 
 def normalise_contrast(images, device=0):
@@ -80,22 +139,88 @@ def normalise_contrast(images, device=0):
     return out[0] if single else out
 
 
+def rescale_frames(images, scale_down_factor, device=0):
+    """``downsample`` of ``load_frames`` (frames_io.py:99-101): every frame through scikit-image 0.13's
+    ``rescale(img, 1.0 / scale_down_factor, preserve_range=True, mode='constant')`` -- bilinear, zero outside the
+    image, no anti-aliasing, clipped to the input range -- on the GPU (``hsm_rescale_frames``; parity with
+    scikit-image unpinned, see csrc/raster.cuh).  As in the reference, the two factors are handed to ``rescale`` in
+    the order they are configured (x, y) and ``rescale`` applies them as (row, column) scales."""
+    images = np.asarray(images)
+    single = images.ndim == 2
+    stack = np.ascontiguousarray(images[None] if single else images, dtype=np.float64)       # preserve_range
+    scale = 1.0 / np.asarray(scale_down_factor, dtype=np.float64)
+    row_scale, col_scale = (scale[0], scale[1]) if scale.size > 1 else (scale.item(), scale.item())
+    out_rows, out_cols = int(np.round(row_scale * stack.shape[1])), int(np.round(col_scale * stack.shape[2]))
+    out = np.empty((stack.shape[0], out_rows, out_cols), dtype=np.float64)
+    ptr = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    _capi.check(_capi.lib().hsm_rescale_frames(stack.shape[0], stack.shape[1], stack.shape[2], ptr(stack), out_rows,
+                                               out_cols, ptr(out), int(device)))
+    return out[0] if single else out
+
+
 def prepare_frames(images, crop_region=None, resolution=None, scale_down_factor=(1, 1), adjust_contrast=False,
                    device=0):
     """The array part of ``load_frames`` (frames_io.py:91-131): crop every frame to ``resolution`` =
-    (width, height) at ``crop_region`` = (column, row) of the top-left corner, then (optionally) stretch each
-    frame's contrast to [0, 1] on the GPU.  Down-scaling (``skimage.transform.rescale``, frames_io.py:99-101)
-    is an un-vendored third-party resampler whose output cannot be pinned here, so any
-    factor other than (1, 1) is refused rather than approximated."""
-    if tuple(int(f) for f in scale_down_factor) != (1, 1):
-        raise NotImplementedError("scale_down_factor != (1, 1): skimage.rescale semantics are not reproduced")
+    (width, height) at ``crop_region`` = (column, row) of the top-left corner, down-scale it
+    (``rescale_frames``; the reference calls ``rescale`` even for a factor of (1, 1), which only converts to
+    float64), then (optionally) stretch each frame's contrast to [0, 1] -- all on the GPU."""
     images = np.asarray(images)
     if images.ndim == 2:
         images = images[None]
     if crop_region is not None and resolution is not None:
         col_start, row_start = crop_region                      # frames_io.py:91-95: x, y order
         dx, dy = resolution
-        images = images[:, row_start:row_start + dy, col_start:col_start + dx]
+        if col_start or row_start or dx or dy:                  # frames_io.py:126-129: all zero = no crop
+            images = images[:, row_start:row_start + dy, col_start:col_start + dx]
+    if tuple(float(f) for f in np.asarray(scale_down_factor).reshape(-1)) != (1.0, 1.0):
+        images = rescale_frames(images, scale_down_factor, device=device)
+    else:
+        images = np.ascontiguousarray(images, dtype=np.float64)
     if adjust_contrast:
         return normalise_contrast(images, device=device)
-    return np.ascontiguousarray(images)
+    return images
+
+
+class OpticalFlowPixelCorrection(object):
+    """Prior adjustment by event optical flow (stereovis/spiking/optical_flow_correction.py:12-88).
+
+    ``adjust`` reproduces the reference AS WRITTEN, including the defect its own FIXME (line 69) names: the
+    velocity field it fits is never used -- the one-pixel shift of every prior pixel comes from the compass
+    direction of the pixel's own (column, row) position.  The result therefore depends only on the prior frames,
+    and ``adjust`` runs one small kernel (``hsm_adjust_priors``) instead of a least-squares fit per event; the
+    constructor keeps the reference's arguments and its per-frame event segmentation so that
+    ``compute_velocity_field`` stays available to callers that want the field itself."""
+
+    def __init__(self, resolution, reference_events, buffer_pivots=None, buffer_interval=50, algorithm="vvf",
+                 device=0):
+        self.resolution = resolution
+        self.device = int(device)
+        if algorithm != "vvf":
+            raise NotImplementedError("Only VRF is supported.")                 # optical_flow_correction.py:28
+        reference_events = np.asarray(reference_events)
+        indices_frames, _ = split_frames_by_time(ts=reference_events[:, 0], time_interval=buffer_interval,
+                                                 pivots=buffer_pivots)
+        self.reference_frames_indices = indices_frames
+        self.reference_events = reference_events
+        self.buffer_interval = buffer_interval
+
+    def compute_velocity_field(self, timespace_frame, assume_sorted=False):
+        from .flow import VelocityVectorField
+        field = VelocityVectorField(time_interval=self.buffer_interval, neighbourhood_size=(3, 3),
+                                    rejection_threshold=0.005, convergence_threshold=1e-5, max_iter_steps=5,
+                                    min_num_events_in_timespace_interval=10, device=self.device)
+        return field.fit_velocity_field(timespace_frame, assume_sorted=assume_sorted,
+                                        concatenate_polarity_groups=False)
+
+    def adjust(self, event_frames, prior_nondata_value=-1, time_arrow=+1):
+        event_frames = np.asarray(event_frames)
+        n_frames = len(self.reference_frames_indices)
+        assert len(event_frames) == n_frames, "Mismatching reference and unadjusted target " \
+            "frames, {} and {} frames respecively".format(n_frames, len(event_frames))
+        stack = np.ascontiguousarray(event_frames, dtype=np.float64)
+        assert stack.shape[1:] == (self.resolution[1], self.resolution[0])
+        out = np.empty(stack.shape, dtype=np.float32)
+        ptr = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+        _capi.check(_capi.lib().hsm_adjust_priors(stack.shape[0], stack.shape[1], stack.shape[2], ptr(stack),
+                                                  float(prior_nondata_value), int(time_arrow), ptr(out), self.device))
+        return out

@@ -197,15 +197,27 @@ int hsm_get_stats(hsm_matcher *m, hsm_stats *out);
 int hsm_reset_stats(hsm_matcher *m);
 
 /*
- * Prior rasterisation (next row N2): replaces the scatter of generate_frames_from_spikes
- * (stereovis/utils/frames_io.py:239-244).  Events are given in the order the reference would write
- * them (frames_io.py:184-204 is done by the host): x, y pixel coordinates (already wrapped into
- * [0, cols) / [0, rows)), z the value, frame the destination frame.  Later events overwrite earlier
- * ones on the same pixel of the same frame; untouched pixels get `fill`.  out: n_frames x rows x cols
- * float64 on the host.  All arrays are host arrays.
+ * Prior rasterisation on the device (next row N2): replaces split_frames_by_time + generate_frames_from_spikes
+ * (stereovis/utils/frames_io.py:184-248), the producer of the matcher's `prior` input
+ * (hybrid_stereo.py:169-176).  Frame f collects the events with lo[f] <= t <= hi[f] (hi_inclusive != 0; with
+ * pivots: lo = tick - time_interval, hi = tick, frames_io.py:200-202) or lo[f] <= t < hi[f] (the wrap-around
+ * frames of frames_io.py:193-198); a pixel gets the value z of the LATEST such event that hit it (numpy's fancy
+ * assignment in chronological order, frames_io.py:239-244; among equal timestamps the later array position
+ * wins), `fill` if none did.  x / y follow numpy index semantics (negative wraps once, otherwise out of range
+ * -> HSM_ERR_ARG, the reference's IndexError).  All inputs are host arrays.  Outputs (either may be NULL):
+ *   frames_out     host, n_frames x rows x cols float64 -- what the reference function returns;
+ *   labels_device  DEVICE, n_frames x rows x cols int32 -- exact integers as they are, everything else -1
+ *                  (`prior == l` of mrf.py:57 is preserved); pass it to hsm_lbp / hsm_init_fields as the prior
+ *                  with prior_dtype HSM_I32 and on_device 2 (or 1): the priors never visit the host.
  */
-int hsm_rasterise_events(size_t n_events, const int *x, const int *y, const double *z, const int *frame,
-                         int n_frames, int rows, int cols, double fill, double *out, int device);
+int hsm_rasterise_events(size_t n_events, const int32_t *x, const int32_t *y, const double *t, const double *z,
+                         int n_frames, const double *lo, const double *hi, int hi_inclusive, int rows, int cols,
+                         double fill, double *frames_out, int32_t *labels_device, int device);
+
+/* Plain device memory for buffers that travel between entry points (e.g. labels_device above). */
+int hsm_device_alloc(size_t bytes, int device, void **out);
+int hsm_device_free(void *p, int device);
+int hsm_device_read(void *dst_host, const void *src_device, size_t bytes, int device);
 
 /*
  * Frame pre-processing (next row N3): per-frame min-max contrast normalisation in float64, replaces
@@ -213,6 +225,27 @@ int hsm_rasterise_events(size_t n_events, const int *x, const int *y, const doub
  * hybrid_stereo.py:90-103).  in/out: n_frames x rows x cols float64 host arrays (may alias).
  */
 int hsm_normalise_contrast(int n_frames, int rows, int cols, const double *in, double *out, int device);
+
+/*
+ * Frame pre-processing (next row N3), down-scaling: replaces load_frames' `downsample`
+ * (stereovis/utils/frames_io.py:99-101) = skimage.transform.rescale(img, 1 / factor, preserve_range=True,
+ * mode='constant') of scikit-image 0.13.0: bilinear, out-of-image neighbours count as 0, no anti-aliasing,
+ * clipped to the input's range.  in: n_frames x rows x cols, out: n_frames x out_rows x out_cols, float64 host
+ * arrays.  Parity with scikit-image is unpinned (not installable here); see raster.cuh for the one known
+ * deviation (exact instead of least-squares-estimated affine coefficients).
+ */
+int hsm_rescale_frames(int n_frames, int rows, int cols, const double *in, int out_rows, int out_cols, double *out,
+                       int device);
+
+/*
+ * Prior adjustment (next row N4): replaces OpticalFlowPixelCorrection.adjust
+ * (stereovis/spiking/optical_flow_correction.py:34-88) as written, including the defect its FIXME (:69) names --
+ * the shift of a prior pixel is taken from the compass direction of its own (col, row) position, not from the
+ * fitted velocity field.  prior: n_frames x rows x cols float64 (values >= 0 move), out: float32, host arrays;
+ * time_arrow = +1 / -1.
+ */
+int hsm_adjust_priors(int n_frames, int rows, int cols, const double *prior, double nondata, int time_arrow, float *out,
+                      int device);
 
 /*
  * Self-test of the shared-reciprocal division used by the fused kernel: a4 holds n x 4

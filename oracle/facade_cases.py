@@ -33,6 +33,34 @@ RASTER_CASES = [
 ]
 
 
+# OpticalFlowPixelCorrection.adjust (optical_flow_correction.py:34-88): reference events (t, x, y, polarity) per
+# buffer window + prior frames to adjust
+ADJUST_CASES = [
+    dict(name="a01_adjust_predictive", seed=21, res=(20, 14), n_events=260, levels=9, pivots=[60.0, 120.0, 180.0],
+         interval=50, time_arrow=+1, density=0.3),
+    dict(name="a02_adjust_retrospective", seed=22, res=(20, 14), n_events=260, levels=9, pivots=[60.0, 120.0],
+         interval=50, time_arrow=-1, density=0.3),
+    dict(name="a03_adjust_dense_collisions", seed=23, res=(33, 27), n_events=200, levels=20, pivots=[80.0, 160.0],
+         interval=60, time_arrow=+1, density=0.9),
+    dict(name="a04_adjust_checkerboard_scale", seed=24, res=(80, 60), n_events=150, levels=22, pivots=[50.0],
+         interval=50, time_arrow=+1, density=0.1),
+]
+
+
+def adjust_inputs(case):
+    """(reference_events (N, 4): t, x, y, polarity; prior frames (F, rows, cols) float64 with -1 = none)."""
+    rng = np.random.default_rng(case["seed"])
+    cols, rows = case["res"]
+    n = case["n_events"]
+    events = np.stack([np.sort(rng.random(n) * (max(case["pivots"]) + 5.0)), rng.integers(0, cols, n).astype(float),
+                       rng.integers(0, rows, n).astype(float), rng.integers(0, 2, n).astype(float)], axis=1)
+    events = events[rng.permutation(n)]
+    frames = np.full((len(case["pivots"]), rows, cols), -1.0)
+    mask = rng.random(frames.shape) < case["density"]
+    frames[mask] = rng.integers(0, case["levels"], int(mask.sum()))
+    return events, frames
+
+
 def facade_inputs(case):
     """(lefts, rights, timestamps, prior_info or None) of a façade case."""
     import importlib

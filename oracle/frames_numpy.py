@@ -3,9 +3,9 @@ TEST INFRASTRUCTURE ONLY -- the checker for hybrid-stereo-matching_b200/priors.p
 import numpy as np
 
 
-def split(ts, start_time=0, time_interval=100, pivots=None):
+def split(ts, start_time=0, time_interval=100, pivots=None, sort_kind=None):
     ts = np.asarray(ts)
-    order = np.argsort(ts)
+    order = np.argsort(ts, kind=sort_kind)
     times = ts[order]
     keep = times >= start_time
     times = times[keep]
@@ -18,10 +18,13 @@ def split(ts, start_time=0, time_interval=100, pivots=None):
     return groups, pivots
 
 
-def rasterise(resolution, xs, ys, ts, zs, start_time=0, time_interval=100, pivots=None, non_pixel_value="nan"):
+def rasterise(resolution, xs, ys, ts, zs, start_time=0, time_interval=100, pivots=None, non_pixel_value="nan",
+              sort_kind=None):
+    """``sort_kind``: None = numpy's default like the reference (ties in an implementation-defined order),
+    "stable" = ties in input order (what the product defines)."""
     xs, ys = np.asarray(xs).astype(int), np.asarray(ys).astype(int)
     ts, zs = np.asarray(ts), np.asarray(zs)
-    groups, timestamps = split(ts, start_time, time_interval, pivots)
+    groups, timestamps = split(ts, start_time, time_interval, pivots, sort_kind)
     n_cols, n_rows = resolution
     frames = np.ones((len(groups), n_rows, n_cols)) * float(non_pixel_value)
     for i, inds in enumerate(groups):

@@ -7,7 +7,7 @@ import sys
 import numpy as np
 
 from . import facade_cases as F
-from . import facade_ref, frames_ref
+from . import facade_ref, flow_ref, frames_ref
 
 
 def main():
@@ -36,6 +36,15 @@ def main():
             arrays["stamps_%s" % fill] = np.asarray(stamps)
         np.savez_compressed(F.fixture_path(case), **arrays)
         print("%-36s %s" % (case["name"], arrays["frames_-1"].shape), flush=True)
+    _, correction_class = flow_ref.load()
+    for case in F.ADJUST_CASES:
+        events, frames = F.adjust_inputs(case)
+        correction = correction_class(case["res"], events, buffer_pivots=case["pivots"],
+                                      buffer_interval=case["interval"])
+        adjusted = correction.adjust(frames, prior_nondata_value=-1, time_arrow=case["time_arrow"])
+        np.savez_compressed(F.fixture_path(case), adjusted=adjusted, dtype=np.asarray(str(adjusted.dtype)))
+        print("%-36s %s %s moved %d" % (case["name"], adjusted.shape, adjusted.dtype,
+                                        int((adjusted != frames).sum())), flush=True)
     return 0
 
 

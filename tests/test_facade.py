@@ -1,6 +1,8 @@
-"""The façade above the hot path (stereo_framebased.py:15-101 restated): prior selection by
-timestamp, call pattern, result stacking -- host logic tested on CPU with the oracle as the matcher;
-the GPU variant checks the batched CUDA path against the same sequence of oracle calls."""
+"""The façade above the hot path (stereo_framebased.py:15-101): prior selection by timestamp, call
+pattern, result stacking.  Pinned to outputs of the REAL ``FramebasedStereoMatching`` (tests/golden/f*.npz,
+written by oracle/make_golden_facade.py, which executes the reference class with the reference matcher):
+on CPU the product façade runs with the numpy oracle as its matcher, on the GPU with the CUDA matcher; in the
+build container the real class is also run live."""
 import sys
 
 import numpy as np
@@ -110,3 +112,50 @@ def test_online_iteration_budget_rule():
                     want = min(max_iter, max(min_iter, want))
                     assert framed.next_n_iter(n_iter, duration, budget, min_iter, max_iter) == want
     assert framed.next_n_iter(3, 1.0, 50.0, 1, 10, adaptive=False) == 10
+
+
+# ---- against the real reference class --------------------------------------------------------------
+from oracle import facade_cases as F                                   # noqa: E402
+from oracle import facade_ref                                          # noqa: E402
+
+
+def _run_product_facade(hsm, case, **facade_kwargs):
+    lefts, rights, ts, info = F.facade_inputs(case)
+    facade = hsm.FramebasedStereoMatching((case["cols"], case["rows"]), case["levels"],
+                                          inputs={"left": lefts, "right": rights, "ts": ts}, **facade_kwargs)
+    if case["priors"] == "online":
+        for i in range(case["n"]):
+            facade.run_one_frame(lefts[i], rights[i], info["priors"][i], n_iter=3 + i)
+    else:
+        facade.run(info)
+    return facade
+
+
+@pytest.mark.parametrize("case", F.FACADE_CASES, ids=[c["name"] for c in F.FACADE_CASES])
+def test_facade_host_logic_matches_reference_fixture(hsm, case):
+    data = np.load(F.fixture_path(case), allow_pickle=False)
+    facade = _run_product_facade(hsm, case, matcher_factory=lambda dim, lv: mrf_numpy.OracleMRF(dim, lv))
+    out = facade.get_output()
+    assert str(out.dtype) == str(data["dtype"]) and out.shape == data["depth"].shape
+    assert np.array_equal(out, data["depth"])
+    assert np.array_equal(facade.get_timestamps(), data["timestamps"])
+
+
+@pytest.mark.skipif(not facade_ref.available(), reason="reference checkout not present")
+def test_fixtures_are_what_the_real_class_returns():
+    reference = facade_ref.load()
+    case = F.FACADE_CASES[1]
+    lefts, rights, ts, info = F.facade_inputs(case)
+    facade = reference((case["cols"], case["rows"]), case["levels"], inputs={"left": lefts, "right": rights, "ts": ts})
+    facade.run(info)
+    assert np.array_equal(facade.get_output(), np.load(F.fixture_path(case))["depth"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("capacity", [2, 64])
+@pytest.mark.parametrize("case", F.FACADE_CASES, ids=[c["name"] for c in F.FACADE_CASES])
+def test_facade_cuda_matches_reference_fixture(hsm, case, capacity):
+    data = np.load(F.fixture_path(case), allow_pickle=False)
+    facade = _run_product_facade(hsm, case, capacity=capacity)
+    out = facade.get_output()
+    assert str(out.dtype) == str(data["dtype"]) and np.array_equal(out, data["depth"])

@@ -192,3 +192,53 @@ def test_full_size_properties_c1_batch(hsm):
         assert np.all((peak == 1.0) | (peak == 0.0)), name
     assert not planes["south"][:, 0, :].any() and not planes["north"][:, -1, :].any()
     assert not planes["west"][:, :, -1].any() and not planes["east"][:, :, 0].any()
+
+
+@pytest.mark.parametrize("lane_config,max_levels", [(10, 20), (11, 24), (12, 40), (13, 48)],
+                         ids=["5x1", "6x1", "5x2", "6x2"])
+@pytest.mark.parametrize("algorithm", [5, 6], ids=["tmast", "flow"])
+def test_non_power_of_two_lane_layouts(hsm, lane_config, max_levels, algorithm):
+    """Lane layouts with 5 / 6 lanes per pixel (HSM_OPT_LANE_CONFIG 10..13; chosen automatically for D = 17..24 and
+    33..48, e.g. the shipped max_disparity 20 and 22): every fixture whose disparity count they cover, including
+    counts that leave some of their chunks partly or wholly unused, against the reference's planes and labels."""
+    from importlib import import_module
+    capi = import_module("hybrid-stereo-matching_b200._capi")
+    todo = [(c, True) for c in C.SMALL_CASES if c["levels"] <= max_levels] + \
+           [(c, False) for c in C.HUGE_CASES if c["levels"] <= max_levels and c["levels"] > max_levels - 8]
+
+    def make(dim, levels):
+        m = hsm.StereoMRF(tuple(dim), levels)
+        m.set_option(capi.OPT_ALGORITHM, algorithm)
+        m.set_option(capi.OPT_LANE_CONFIG, lane_config)
+        return m
+    assert len(todo) >= 10
+    for case, small in todo:
+        labels, planes = C.run_case(make, case)
+        data, meta = C.load_fixture(case)
+        assert np.array_equal(labels, data["labels"]), case["name"]
+        for name, plane in planes.items():
+            assert C.plane_sha1(plane) == meta["plane_sha1"][name], (case["name"], name)
+            if small:
+                assert np.array_equal(plane, data["plane_" + name], equal_nan=True), (case["name"], name)
+
+
+def test_first_iteration_reads_no_planes_but_state_reads_back_as_zero(hsm):
+    """hsm_init_fields(reinit) only records that the messages are zero; read-backs before any iteration, and
+    n_iter = 0, must still see real zeros -- also right after a run that left non-zero planes behind."""
+    case = C.SMALL_CASES[3]
+    left, right, prior, kwargs = C.case_inputs(case, 0)
+    m = hsm.StereoMRF(left.shape, case["levels"])
+    m.lbp(left, right, prior, prior_trust_factor=1.0, prior_influence_mode="adaptive", n_iter=4)
+    m.loop_belief(left, right, prior, n_iter=0)
+    for name, plane in m._message_field.items():
+        if name != "data":
+            assert not plane.any(), name
+    want = mrf_c.OracleMRFC(left.shape, case["levels"])
+    want_labels = want.lbp(left, right, prior, n_iter=0)
+    assert np.array_equal(m.lbp(left, right, prior, n_iter=0), want_labels)
+    # and a one-iteration run (the zero-input launch is also the finalising one)
+    got = m.lbp(left, right, prior, prior_trust_factor=1.0, prior_influence_mode="adaptive", n_iter=1)
+    assert np.array_equal(got, want.lbp(left, right, prior, prior_trust_factor=1.0,
+                                        prior_influence_mode="adaptive", n_iter=1))
+    for name, plane in want._message_field.items():
+        assert np.array_equal(m._message_field[name], plane), name
