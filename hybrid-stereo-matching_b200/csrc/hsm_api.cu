@@ -365,6 +365,22 @@ int make_plane_map(const hsm_matcher *m, CUtensorMap *map, float *plane, int px)
     return HSM_OK;
 }
 
+// 4-D map (Dp, cols, 1, 1) over ONE row of a neighbouring GPU's plane (its ghost row; peer-mapped memory)
+int make_ghost_map(const hsm_matcher *m, CUtensorMap *map, float *row, int px)
+{
+    EncodeTiledFn encode;
+    HSM_TRY(encode_fn(&encode));
+    const cuuint64_t dims[4] = {(cuuint64_t)m->Dp, (cuuint64_t)m->W, 1, 1};
+    const cuuint64_t strides[3] = {(cuuint64_t)m->Dp * 4, (cuuint64_t)m->W * m->Dp * 4, (cuuint64_t)m->W * m->Dp * 4};
+    const cuuint32_t box[4] = {(cuuint32_t)m->Dp, (cuuint32_t)px, 1, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult rc = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, row, dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS) return fail(HSM_ERR_CUDA, "cuTensorMapEncodeTiled (ghost row) failed with code %d", (int)rc);
+    return HSM_OK;
+}
+
 // 3-D map (cols, valid rows, frames) over a device image with row pitch Wp; box = `box` columns.
 int make_image_map(const hsm_matcher *m, CUtensorMap *map, void *image, bool is_int, int box)
 {
@@ -455,6 +471,15 @@ int ensure_maps(hsm_matcher *m)
         HSM_TRY(make_image_map(m, &m->st.tmI.L, m->L, false, px5 + 4));
         HSM_TRY(make_image_map(m, &m->st.tmI.R, m->R, false, rbox5));
         HSM_TRY(make_image_map(m, &m->st.tmI.P, m->P, true, px5 + 4));
+        for (int side = 0; side < 2; ++side) {
+            hsm_matcher::Peer &p = m->peer[side];
+            if (!p.attached) continue;
+            for (int i = 0; i < 2; ++i) {
+                HSM_TRY(make_ghost_map(m, &p.psW[i], p.Wm[i] + p.ghost_off, px5 - 2));
+                HSM_TRY(make_ghost_map(m, &p.psN[i], p.Nm[i] + p.ghost_off, px5 - 2));
+                HSM_TRY(make_ghost_map(m, &p.psE[i], p.Em[i] + p.ghost_off, px5 - 2));
+            }
+        }
     }
     m->maps_valid = true;
     return HSM_OK;
@@ -610,6 +635,7 @@ int hsm_destroy(hsm_matcher *m)
         for (auto &pr : m->pending) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
         for (auto &pr : m->pool) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
         cudaFree(m->arena);
+        if (m->host_stage) cudaFreeHost(m->host_stage);
         if (m->flow_state) cudaFree(m->flow_state);
         if (m->aux_stream) cudaStreamDestroy(m->aux_stream);
         if (m->fork_event) cudaEventDestroy(m->fork_event);
@@ -923,10 +949,69 @@ int hsm_readout(hsm_matcher *m, int64_t *labels, int on_device, int async)
     return HSM_OK;
 }
 
+// hsm_lbp for a SMALL batch of host arrays that the caller waits for (the reference's own call: one frame pair,
+// numpy arrays, online_processing.py:128).  Such a call is made of latencies, not bandwidth: pageable copies
+// stall the calling thread one by one, and every launch costs microseconds.  Here the inputs are copied into a
+// page-locked block owned by the matcher (a memcpy of a few hundred KB), go up as asynchronous copies, ONE
+// kernel converts both images and the prior, and the labels come back through the same block.
+int lbp_small_host(hsm_matcher *m, int n_frames, const void *left, const void *right, int image_dtype,
+                   const void *prior, int prior_dtype, int prior_mode, float keep_f32, double keep_f64, int n_iter,
+                   int64_t *labels)
+{
+    HSM_TRY(ensure_ready(m));
+    const size_t n = (size_t)n_frames * m->H * m->W;
+    const size_t img_bytes = n * dtype_size(image_dtype);
+    const bool with_prior = prior != nullptr && prior_mode != HSM_PRIOR_NONE;
+    const size_t prior_bytes = with_prior ? n * dtype_size(prior_dtype) : 0;
+    const size_t off_r = align_up(img_bytes, 256), off_p = off_r + align_up(img_bytes, 256);
+    const size_t off_out = off_p + align_up(prior_bytes, 256), total = off_out + n * sizeof(int64_t);
+    if (m->host_stage_bytes < total) {
+        if (m->host_stage) CUDA_TRY(cudaFreeHost(m->host_stage));
+        m->host_stage = nullptr; m->host_stage_bytes = 0;
+        CUDA_TRY(cudaHostAlloc((void **)&m->host_stage, total, cudaHostAllocDefault));
+        m->host_stage_bytes = total;
+    }
+    char *h = m->host_stage;
+    memcpy(h, left, img_bytes);
+    memcpy(h + off_r, right, img_bytes);
+    if (with_prior) memcpy(h + off_p, prior, prior_bytes);
+    CUDA_TRY(cudaMemcpyAsync(m->stage[0], h, img_bytes, cudaMemcpyHostToDevice, m->stream));
+    CUDA_TRY(cudaMemcpyAsync(m->stage[1], h + off_r, img_bytes, cudaMemcpyHostToDevice, m->stream));
+    if (with_prior) CUDA_TRY(cudaMemcpyAsync(m->stage[2], h + off_p, prior_bytes, cudaMemcpyHostToDevice, m->stream));
+    m->frames = n_frames;
+    m->have_prior = with_prior;
+    m->blend.mode = with_prior ? prior_mode : kPriorNone;
+    m->blend.keep32 = keep_f32;
+    m->blend.keep64 = keep_f64;
+    const int blocks = (int)std::min<size_t>((n + 255) / 256, (size_t)m->sm_count * 16);
+    k_convert_inputs<<<blocks, 256, 0, m->stream>>>(m->stage[0], m->stage[1], image_dtype,
+                                                    with_prior ? m->stage[2] : nullptr, prior_dtype, m->L, m->R, m->P, n,
+                                                    m->D, m->W, m->Wp);
+    HSM_TRY(check_launch(m, "k_convert_inputs"));
+    m->zero_messages = true;                                 // mrf.py:165: lbp always re-initialises
+    m->s_valid = true;
+    m->have_fields = true;
+    m->dt_valid = false;
+    HSM_TRY(hsm_iterate(m, n_iter, 1));
+    HSM_TRY(hsm_readout(m, (int64_t *)m->labels, 1, 1));     // labels stay on the device ...
+    CUDA_TRY(cudaMemcpyAsync(h + off_out, m->labels, n * sizeof(int64_t), cudaMemcpyDeviceToHost, m->stream));
+    CUDA_TRY(cudaStreamSynchronize(m->stream));               // ... and come back through the page-locked block
+    memcpy(labels, h + off_out, n * sizeof(int64_t));
+    return HSM_OK;
+}
+
 int hsm_lbp(hsm_matcher *m, int n_frames, const void *left, const void *right, int image_dtype, const void *prior,
             int prior_dtype, int prior_mode, float keep_f32, double keep_f64, int n_iter, int64_t *labels,
             int on_device, int async)
 {
+    if (m && on_device == 0 && async == 0 && left && right && labels && n_frames >= 1 && n_frames <= m->cap &&
+        n_iter >= 0 && (image_dtype == HSM_F32 || image_dtype == HSM_F64) &&
+        prior_mode >= HSM_PRIOR_NONE && prior_mode <= HSM_PRIOR_CONST_F64 && (!prior || dtype_size(prior_dtype) != 0) &&
+        (size_t)n_frames * m->H * m->W <= (size_t)1 << 19) {
+        DeviceScope scope(m->device);
+        return lbp_small_host(m, n_frames, left, right, image_dtype, prior, prior_dtype, prior_mode, keep_f32, keep_f64,
+                              n_iter, labels);
+    }
     // one queue of work, one synchronisation (in the readout, unless async): with an asynchronous readout the
     // host buffers must stay valid until hsm_sync, so only then are they released here
     // async == 2: the caller keeps ALL host buffers valid until hsm_sync -- nothing waits here at all
@@ -1067,6 +1152,7 @@ int hsm_peer_attach(hsm_matcher *m, int side, const hsm_peer_info *peer, int sam
     p.ghost_flags = (unsigned *)(base + peer->off_mailbox) + hsm_matcher::kGhostBase +
                     (1 - side) * hsm_matcher::kGhostStride;
     p.attached = true;
+    m->maps_valid = false;               // the ghost-row store maps are built with the other tensor maps
     return HSM_OK;
 }
 

@@ -19,6 +19,7 @@ struct FlowMaps {                               // 16 tensor maps = 2 KB of kern
     CUtensorMap tmW[2], tmN[2], tmE[2];         // loads from plane generation 0 / 1
     CUtensorMap tsW[2], tsN[2], tsE[2];         // stores into plane generation 0 / 1
     CUtensorMap tmD, tmL, tmR, tmP;
+    PushMaps push[2];                           // the neighbours' ghost rows, per plane generation (PUSH kernels)
 };
 
 struct FlowArgs {
@@ -159,7 +160,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? (VPL == 1 ? HSM_TMA_MIN_BLOCKS
                                                             &maps.tmL, &maps.tmR, &maps.tmP, &maps.tsW[out],
                                                             &maps.tsN[out], &maps.tsE[out], g, a, stages, bx, by, frame,
                                                             store_s, smem_raw, stage, phase, first, pp,
-                                                            a.zero_in != 0 && it == 0, &pending);
+                                                            a.zero_in != 0 && it == 0, &pending, &maps.push[out]);
         first = false;
         pending.local = tile + by * f.strips + bx;
         pending.local_value = (unsigned)it + 1u;

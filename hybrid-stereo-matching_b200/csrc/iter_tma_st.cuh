@@ -62,6 +62,15 @@ __device__ __forceinline__ void flow_publish(const FlowPending &p)
     }
 }
 
+// Row-band mode (PUSH kernels): tensor maps over the ghost rows of the neighbouring GPUs' planes (side 0 = the
+// band above, 1 = the band below; dims (Dp, cols, 1, 1) based at the ghost row, peer-mapped memory).  The first /
+// last owned row of a new plane is staged in shared memory for its local bulk store anyway, so the halo push is
+// ONE MORE bulk tensor store of the same staging buffer, issued by the same thread: no other thread of the CTA
+// executes a single instruction for it (per-thread peer stores cost ~10 % of the kernel).
+struct PushMaps {
+    CUtensorMap W[2], N[2], E[2];
+};
+
 // One task of the fused iteration: strip `bx`, band `by` of frame `frame`.  Shared by the one-launch-per-
 // iteration kernel (k_iter_tmast: one task per CTA) and the persistent dataflow kernel (iter_flow.cuh: a CTA
 // runs task after task; FLOW = true).  `stage` / `phase` are the position in the ring of row stages; they carry
@@ -77,7 +86,7 @@ __device__ __forceinline__ void tmast_task(const CUtensorMap *tmW, const CUtenso
                                            const int bx, const int by, const int frame, const bool store_s_arg,
                                            unsigned char *smem_raw, int &stage, uint32_t &phase, const bool first_task,
                                            const PushPtrs &pp, const bool zero_in,
-                                           const FlowPending *publish = nullptr)
+                                           const FlowPending *publish = nullptr, const PushMaps *pmaps = nullptr)
 {
     using SL = StageLayout<LPP, VPL, NT>;
     using PM = PixelMap<LPP, NT>;
@@ -198,8 +207,15 @@ __device__ __forceinline__ void tmast_task(const CUtensorMap *tmW, const CUtenso
             if (FULL || ln.active[v]) slot[buf * ost_f4 + v * LPP] = val.q[v];
     };
     // thread 0: one bulk tensor store per plane-row; out-of-image columns are clipped by the TMA unit
-    auto tma_store_row = [&](const CUtensorMap *map, int plane, int buf, int y) {
+    // `push` = the neighbours' ghost-row maps of the same plane: a boundary row also goes there
+    auto tma_store_row = [&](const CUtensorMap *map, const CUtensorMap *push, int plane, int buf, int y) {
         tma_store_4d(map, ost + (2u * plane + buf) * ost_bytes, 0, xs0, y - g.vlo, frame_mem);
+#ifndef HSM_PUSH_PLAIN_STORES
+        if constexpr (PUSH) {
+            if (y == a.olo && pp.W[0] != nullptr) tma_store_4d(&push[0], ost + (2u * plane + buf) * ost_bytes, 0, xs0, 0, 0);
+            if (y == a.ohi && pp.W[1] != nullptr) tma_store_4d(&push[1], ost + (2u * plane + buf) * ost_bytes, 0, xs0, 0, 0);
+        }
+#endif
     };
 
     // ---- consumer side ------------------------------------------------------------------------
@@ -254,6 +270,7 @@ __device__ __forceinline__ void tmast_task(const CUtensorMap *tmW, const CUtenso
     };
     // peer-to-peer halo push: row `row` of a new plane also goes to the neighbouring GPU's ghost row
     // (plain stores through the peer mapping; the TMA store maps only cover this GPU's planes)
+#ifdef HSM_PUSH_PLAIN_STORES                // emergency build: per-thread peer stores instead of the bulk tensor push
     const unsigned lane_col = (unsigned)x * (unsigned)g.Dp + 4u * (unsigned)ln.c;
     auto push_row = [&](float *const (&peer)[2], int row, int dx, bool mine, const Vec<VPL> &val) {
         if (!mine) return;
@@ -261,6 +278,7 @@ __device__ __forceinline__ void tmast_task(const CUtensorMap *tmW, const CUtenso
         if (row == a.olo && peer[0] != nullptr) store_at(peer[0], pp.off[0] + col, val);
         if (row == a.ohi && peer[1] != nullptr) store_at(peer[1], pp.off[1] + col, val);
     };
+#endif
 
     // row yb0-1 only contributes S'(yb0)
     {
@@ -319,7 +337,9 @@ __device__ __forceinline__ void tmast_task(const CUtensorMap *tmW, const CUtenso
         for (int v = 0; v < VPL; ++v)
             if (PM::POW2 || pm.real) sts_f4(ex_wr_addr + par * EX_PAR + v * EX_V, t.q[v]);
         if (st_w) stage_out(st_wp, par, t);
+#ifdef HSM_PUSH_PLAIN_STORES
         if constexpr (PUSH) push_row(pp.W, y, -1, st_w && (x - 1) < g.W && y <= yb1, t);
+#endif
         if (STORE_S) {                         // block-uniform: the last iteration only
             if (st_s && y + 1 <= yb1) store_at(Sout, row_off + row_stride, Snext);
         }
@@ -331,8 +351,11 @@ __device__ __forceinline__ void tmast_task(const CUtensorMap *tmW, const CUtenso
         if (tid == 0) {
             const int r = y - yb0 + 1;
             if (r + stages < n_rows) issue(r + stages, stage);
-            if (y <= yb1) tma_store_row(tsW, 0, par, y);
-            if (y > yb0 + 1) { tma_store_row(tsN, 1, par ^ 1, y - 2); tma_store_row(tsE, 2, par ^ 1, y - 2); }
+            if (y <= yb1) tma_store_row(tsW, PUSH ? pmaps->W : nullptr, 0, par, y);
+            if (y > yb0 + 1) {
+                tma_store_row(tsN, PUSH ? pmaps->N : nullptr, 1, par ^ 1, y - 2);
+                tma_store_row(tsE, PUSH ? pmaps->E : nullptr, 2, par ^ 1, y - 2);
+            }
             tma_store_commit();
         }
         if (++stage == stages) { stage = 0; phase ^= 1u; }
@@ -370,8 +393,10 @@ __device__ __forceinline__ void tmast_task(const CUtensorMap *tmW, const CUtenso
         if (upper) {
             if (st_n) stage_out(st_np, par, tn);
             if (st_e) stage_out(st_ep, par, t);
+#ifdef HSM_PUSH_PLAIN_STORES
             if constexpr (PUSH) push_row(pp.N, y - 1, 0, st_n && in_x, tn);
             if constexpr (PUSH) push_row(pp.E, y - 1, +1, st_e && (x + 1) < g.W, t);
+#endif
         }
         row_off += row_stride;
     };
@@ -388,8 +413,8 @@ __device__ __forceinline__ void tmast_task(const CUtensorMap *tmW, const CUtenso
     __syncthreads();
     if (tid == 0) {
         const int last_par = (yb1 + 1 - yb0) & 1;
-        tma_store_row(tsN, 1, last_par, yb1);
-        tma_store_row(tsE, 2, last_par, yb1);
+        tma_store_row(tsN, PUSH ? pmaps->N : nullptr, 1, last_par, yb1);
+        tma_store_row(tsE, PUSH ? pmaps->E : nullptr, 2, last_par, yb1);
         tma_store_commit();
         tma_store_wait_read();                  // (dataflow kernel: completion is awaited by flow_publish)
     }
@@ -401,8 +426,8 @@ __global__ void __launch_bounds__(NT, NT == 256 ? (VPL == 1 ? HSM_TMA_MIN_BLOCKS
                const __grid_constant__ CUtensorMap tmE, const __grid_constant__ CUtensorMap tmD,
                const __grid_constant__ CUtensorMap tmL, const __grid_constant__ CUtensorMap tmR,
                const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUtensorMap tsW,
-               const __grid_constant__ CUtensorMap tsN, const __grid_constant__ CUtensorMap tsE, Geo g, IterArgs a,
-               int stages)
+               const __grid_constant__ CUtensorMap tsN, const __grid_constant__ CUtensorMap tsE,
+               const __grid_constant__ PushMaps pmaps, Geo g, IterArgs a, int stages)
 {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     int stage = 0;
@@ -414,7 +439,9 @@ __global__ void __launch_bounds__(NT, NT == 256 ? (VPL == 1 ? HSM_TMA_MIN_BLOCKS
     }
     tmast_task<LPP, VPL, NT, DT_LOAD, FULL, PUSH, false, STORE_S ? 1 : 0>(
         &tmW, &tmN, &tmE, &tmD, &tmL, &tmR, &tmP, &tsW, &tsN, &tsE, g, a, stages, (int)blockIdx.x, (int)blockIdx.y,
-        a.frame0 + (int)blockIdx.z, STORE_S, smem_raw, stage, phase, true, pp, a.zero_in != 0);
+        a.frame0 + (int)blockIdx.z, STORE_S, smem_raw, stage, phase, true, pp, a.zero_in != 0, nullptr, &pmaps);
+    // a CTA that pushed rows to a neighbour leaves only when those stores have completed
+    if (PUSH && threadIdx.x == 0) tma_store_wait_all();
 }
 
 }  // namespace hsm

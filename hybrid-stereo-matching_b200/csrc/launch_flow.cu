@@ -74,6 +74,13 @@ int launch_flow(hsm_matcher *m, int n_iter, bool finalize, bool *launched)
         maps.tmW[i] = m->st.tmW[i]; maps.tmN[i] = m->st.tmN[i]; maps.tmE[i] = m->st.tmE[i];
         maps.tsW[i] = m->st.tsW[i]; maps.tsN[i] = m->st.tsN[i]; maps.tsE[i] = m->st.tsE[i];
     }
+    memset(maps.push, 0, sizeof maps.push);
+    for (int side = 0; side < 2; ++side)
+        if (HSM_PUSH && m->peer[side].attached)
+            for (int gen = 0; gen < 2; ++gen) {
+                maps.push[gen].W[side] = m->peer[side].psW[gen]; maps.push[gen].N[side] = m->peer[side].psN[gen];
+                maps.push[gen].E[side] = m->peer[side].psE[gen];
+            }
     maps.tmD = m->st.tmD; maps.tmL = m->st.tmI.L; maps.tmR = m->st.tmI.R; maps.tmP = m->st.tmI.P;
     const bool full = (m->D == 4 * LPP * VPL);
 #define HSM_LAUNCH_FLOW(T, F)                                                                                \

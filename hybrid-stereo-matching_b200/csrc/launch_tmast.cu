@@ -39,6 +39,13 @@ int launch_tmast(hsm_matcher *m, bool store_s, bool *launched)
     dim3 grid(strips, bands, m->launch_frames);
     const bool full = (m->D == 4 * LPP * VPL);
     const int in = m->cur, out = m->cur ^ 1;
+    PushMaps pmaps;
+    memset(&pmaps, 0, sizeof pmaps);
+    for (int side = 0; side < 2; ++side)
+        if (HSM_PUSH && m->peer[side].attached) {
+            pmaps.W[side] = m->peer[side].psW[out]; pmaps.N[side] = m->peer[side].psN[out];
+            pmaps.E[side] = m->peer[side].psE[out];
+        }
     cudaLaunchAttribute pdl_attr;
     cudaLaunchConfig_t cfg = launch_config(m, grid, NT, smem, &pdl_attr);
 #define HSM_LAUNCH_TMAST(T, F)                                                                               \
@@ -48,7 +55,7 @@ int launch_tmast(hsm_matcher *m, bool store_s, bool *launched)
         CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
         CUDA_TRY(cudaLaunchKernelEx(&cfg, kernel, m->st.tmW[in], m->st.tmN[in], m->st.tmE[in], m->st.tmD,           \
                                     m->st.tmI.L, m->st.tmI.R, m->st.tmI.P, m->st.tsW[out], m->st.tsN[out],        \
-                                    m->st.tsE[out], g, a, stages));                                            \
+                                    m->st.tsE[out], pmaps, g, a, stages));                                     \
     } while (0)
     if (full) { if (dt_load) HSM_LAUNCH_TMAST(true, true); else HSM_LAUNCH_TMAST(false, true); }
     else { if (dt_load) HSM_LAUNCH_TMAST(true, false); else HSM_LAUNCH_TMAST(false, false); }

@@ -110,6 +110,8 @@ struct hsm_matcher {
     float *L = nullptr, *R = nullptr;
     int *P = nullptr;
     char *stage[3] = {nullptr, nullptr, nullptr};
+    char *host_stage = nullptr;                  // page-locked staging of the small-input path of hsm_lbp
+    size_t host_stage_bytes = 0;
     long long *labels = nullptr;
     int cur = 0;          // which of the double buffers holds the current W, N, E
     int frames = 0;       // frames of the current batch
@@ -137,6 +139,7 @@ struct hsm_matcher {
         unsigned ghost_off = 0;                  // element offset of the neighbour's ghost row inside its planes
         unsigned *ghost_flags = nullptr;         // dataflow kernel: per-strip progress counters in the neighbour's
                                                  // mailbox region that this matcher's boundary tiles publish to
+        CUtensorMap psW[2], psN[2], psE[2];      // store maps over the neighbour's ghost row, per plane generation
     } peer[2];
     // mailbox region in the arena (visible to the neighbours through the IPC mapping):
     //   [0], [1]                     whole-iteration counters written by the band above / below (stream-ordered)
