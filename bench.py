@@ -359,8 +359,15 @@ def band_legs(torch, dist, hsm, rank, world, local_rank, n_iter=50):
     first, last = bands.band_bounds(rows, world, rank)
     engine = bands.CudaBandEngine(rows, cols, levels, first, last, device=local_rank)
     results = {}
-    for exchange in ("p2p", "nccl"):
-        matcher = bands.RowBandMatcher(engine, rank, world, exchange=exchange)
+    capi = import_module("hybrid-stereo-matching_b200._capi")
+    # "p2p": one launch per iteration, neighbours ordered by stream-ordered flags; "p2p_dataflow": ONE persistent
+    # launch per GPU for the whole loop, boundary tiles exchange progress counters through peer memory; "nccl":
+    # pack / send-recv / unpack after every iteration
+    for exchange in ("p2p", "p2p_dataflow", "nccl"):
+        engine.matcher.set_option(capi.OPT_ALGORITHM, 6 if exchange == "p2p_dataflow" else 5)
+        matcher = bands.RowBandMatcher(engine, rank, world, exchange="nccl" if exchange == "nccl" else "p2p")
+        if exchange == "p2p_dataflow":
+            matcher._attached = True                    # the neighbours are still attached from the "p2p" leg
         # parity first: the fixture's own call, gathered labels against the reference's
         labels = matcher.gather(matcher.lbp(left, right, prior, n_iter=fixture_iters, **fkw))
         identical = bool(np.array_equal(labels, want))
@@ -380,10 +387,11 @@ def band_legs(torch, dist, hsm, rank, world, local_rank, n_iter=50):
                              "frac": algo / (ms_iter * 1e-3) / 1e9 / peak,
                              "identical_to_reference": identical, "fixture": "b09_1080p_d256_it2",
                              "rows_per_gpu": last - first + 1}
-        if exchange == "p2p":
+        if exchange == "p2p_dataflow":
             engine.matcher.synchronize()
             dist.barrier()
             engine.detach_peers()
+            engine.matcher.set_option(capi.OPT_ALGORITHM, 5)
     del engine
     torch.cuda.empty_cache()
     return {"shape": "1920x1080xD256", "n_gpus": world,

@@ -297,6 +297,9 @@ int choose_band_rows(const hsm_matcher *m, int strips, int ctas_per_sm)
     const long per_band = (long)strips * m->frames;
     int min_rows = 12;
     while (min_rows > 4 && per_band * ((rows + min_rows - 1) / min_rows) < (long)m->sm_count * 3) min_rows -= 2;
+    // a tiny single frame (the shipped 80x60 configurations): not even one CTA per SM at 4 rows, and an iteration
+    // is the latency of one band -- 2-row bands measured 6.4 us per iteration against 8.7 at 4 rows
+    if (min_rows == 4 && per_band * ((rows + 3) / 4) < (long)m->sm_count) min_rows = 2;
     const bool grouped = m->launch_frames < m->frames;
     const long target = (long)m->sm_count * std::max(1, ctas_per_sm) * (grouped ? 4 : 6);
     long bands = std::max((target + per_band - 1) / per_band, (long)(rows + 63) / 64);
@@ -417,6 +420,7 @@ IterArgs iter_args(hsm_matcher *m, int strips, bool store_s, int ctas_per_sm)
     a.has_prior = m->have_prior ? 1 : 0;
     a.frame0 = m->launch_frame0;
     a.zero_in = m->zero_messages ? 1 : 0;
+    a.labels = nullptr;
     for (int side = 0; side < 2; ++side) {
         const hsm_matcher::Peer &p = m->peer[side];
         a.pushW[side] = p.attached ? p.Wm[m->cur ^ 1] : nullptr;
@@ -776,6 +780,7 @@ int init_fields_impl(hsm_matcher *m, int n_frames, const void *left, const void 
     }
     m->have_fields = true;
     m->dt_valid = false;
+    m->labels_valid = false;
     // a host buffer may be reused by the caller as soon as we return
     if (on_device != 1 && release_host) CUDA_TRY(cudaStreamSynchronize(m->stream));
     return HSM_OK;
@@ -800,6 +805,7 @@ int hsm_iterate(hsm_matcher *m, int n_iter, int finalize)
     if (!m->have_fields) return fail(HSM_ERR_STATE, "hsm_iterate before hsm_init_fields");
     if (n_iter == 0) return HSM_OK;
     HSM_TRY(ensure_ready(m));
+    m->labels_valid = false;
     if (m->algorithm == 0 || m->data_term == 0) HSM_TRY(ensure_data_plane(m));
     // only the TMA-fed kernels can take "all messages are zero" as an out-of-tensor load
     if (!((m->algorithm == 2 || m->algorithm == 5 || m->algorithm == 6) && tma_supported(m)))
@@ -852,6 +858,7 @@ int hsm_iterate(hsm_matcher *m, int n_iter, int finalize)
         CUDA_TRY(cudaStreamWaitEvent(m->aux_stream, m->fork_event, 0));
     }
     const int n_groups = grouped ? 2 : 1;
+    m->labels_fused = false;
     // one kernel per iteration: let the next iteration's CTAs set up while this one drains (with frame
     // groups the other group's CTAs are the better use of those SMs; the peer-to-peer flags sit between
     // the kernels of a stream, so nothing is adjacent there)
@@ -911,6 +918,7 @@ int hsm_iterate(hsm_matcher *m, int n_iter, int finalize)
     m->pending.push_back(ev);
     m->stats.iterations += (uint64_t)n_iter;
     m->s_valid = (m->algorithm == 0) || finalize;
+    m->labels_valid = finalize != 0 && m->labels_fused;
     return HSM_OK;
 }
 
@@ -928,6 +936,11 @@ int hsm_readout(hsm_matcher *m, int64_t *labels, int on_device, int async)
     if (dt_load) HSM_TRY(ensure_data_plane(m));
     long long *dst = on_device ? (long long *)labels : m->labels;
     const int *prior = m->have_prior ? m->P : nullptr;
+    const size_t label_bytes = (size_t)m->frames * m->H * m->W * sizeof(long long);
+    if (m->labels_valid) {                   // fused readout: the finalising launch already wrote m->labels
+        if (on_device && dst != m->labels)
+            CUDA_TRY(cudaMemcpyAsync(dst, m->labels, label_bytes, cudaMemcpyDeviceToDevice, m->stream));
+    } else {
     HSM_DISPATCH(m->cfg, {
         (void)NT;
         const int grid = pixel_grid(m, LPP);
@@ -941,10 +954,8 @@ int hsm_readout(hsm_matcher *m, int64_t *labels, int on_device, int async)
                                                                     m->blend, dst, nullptr);
     });
     HSM_TRY(check_launch(m, "k_readout"));
-    if (!on_device) {
-        const size_t bytes = (size_t)m->frames * m->H * m->W * sizeof(long long);
-        CUDA_TRY(cudaMemcpyAsync(labels, m->labels, bytes, cudaMemcpyDeviceToHost, m->stream));
     }
+    if (!on_device) CUDA_TRY(cudaMemcpyAsync(labels, m->labels, label_bytes, cudaMemcpyDeviceToHost, m->stream));
     if (!async) CUDA_TRY(cudaStreamSynchronize(m->stream));
     return HSM_OK;
 }
@@ -989,6 +1000,7 @@ int lbp_small_host(hsm_matcher *m, int n_frames, const void *left, const void *r
                                                     m->D, m->W, m->Wp);
     HSM_TRY(check_launch(m, "k_convert_inputs"));
     m->zero_messages = true;                                 // mrf.py:165: lbp always re-initialises
+    m->labels_valid = false;
     m->s_valid = true;
     m->have_fields = true;
     m->dt_valid = false;
@@ -1053,6 +1065,7 @@ int hsm_set_plane(hsm_matcher *m, int frame, int which, const float *in)
     if (!in) return fail(HSM_ERR_ARG, "null input");
     HSM_TRY(ensure_ready(m));
     if (m->frames <= frame) m->frames = frame + 1;
+    m->labels_valid = false;
     HSM_TRY(materialise_zero_messages(m));
     float *dst = plane_ptr(m, which) + (size_t)frame * m->H * m->W * m->Dp;
     CUDA_TRY(cudaMemcpy2DAsync(dst, (size_t)m->Dp * 4, in, (size_t)m->D * 4, (size_t)m->D * 4,

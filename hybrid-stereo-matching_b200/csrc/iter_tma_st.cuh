@@ -294,6 +294,35 @@ __device__ __forceinline__ void tmast_task(const CUtensorMap *tmW, const CUtenso
         refill(0);
     }
 
+    // Fused readout (finalising launch of the one-launch-per-iteration kernel only, S_MODE == 1).  The energy of
+    // mrf.py:103, (((S + W) + N) + E) + Dt, of pixel (y-1, x) is ((X(y-1) + N'(y-1, x)) + E'(y-1, x)) + Dt(y-1): the
+    // first three terms are in this thread's registers at step y (X = S' + W' is the carried sum, and X + N' is an
+    // intermediate of U_E anyway); E'(y-1, x) is computed at the same step by the thread of the pixel to the left
+    // and passes through the TMA staging buffer, readable after the next row's barrier.  So the partial sum and the
+    // data term wait one step, then argmin -> int64 label, and the separate pass over all four planes
+    // (k_readout: 16 B per element read again) disappears.
+    constexpr bool READOUT = (S_MODE == 1) && !FLOW;
+    Vec<VPL> Ppend, Dpend;
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) Ppend.q[v] = Dpend.q[v] = zero4();
+    long long *label_row = nullptr;
+    if (READOUT && a.labels != nullptr)
+        label_row = a.labels + ((size_t)frame * g.H + (size_t)(yb0 - 2)) * g.W + x;     // row of step yb0's (absent) label
+    // label of the pixel whose partial energy is pending: E' from staging buffer `buf`, slot of column x
+    auto emit_label = [&](int buf) {
+        Vec<VPL> en;
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) {
+            const float4 e4 = (FULL || ln.active[v]) ? st_ep[buf * ost_f4 + v * LPP - (g.Dp / 4)] : zero4();
+            en.q[v] = add4(add4(Ppend.q[v], e4), Dpend.q[v]);
+        }
+        float best;
+        int arg;
+        lane_argmin<LPP, VPL>(en, ln, best, arg);
+        pixel_argmin<LPP, VPL>(best, arg, ln);
+        if (ln.c == 0 && st_s) *label_row = (long long)arg;
+    };
+
     // One row: Sin = S'(y, x); Xin, Din belong to row y-1; Sout_/Xout/Dout are produced for the next row.
     // The exchange of W' uses a split barrier: arrive after publishing W'(y, x-1), compute S'(y+1)
     // (which does not depend on the neighbour), then wait and pick up W'(y, x).
@@ -359,6 +388,9 @@ __device__ __forceinline__ void tmast_task(const CUtensorMap *tmW, const CUtenso
             tma_store_commit();
         }
         if (++stage == stages) { stage = 0; phase ^= 1u; }
+        if (READOUT) {                         // row y-2: its E' was staged at the previous step (buffer par ^ 1)
+            if (label_row != nullptr && y >= yb0 + 2 && px >= 1) emit_label(par ^ 1);
+        }
         // X = S'(y, x) + W'(y, x)
 #pragma unroll
         for (int v = 0; v < VPL; ++v) Xout.q[v] = add4(Sin.q[v], lds_f4(ex_rd_addr + par * EX_PAR + v * EX_V));
@@ -398,6 +430,11 @@ __device__ __forceinline__ void tmast_task(const CUtensorMap *tmW, const CUtenso
             if constexpr (PUSH) push_row(pp.E, y - 1, +1, st_e && (x + 1) < g.W, t);
 #endif
         }
+        if (READOUT) {                         // partial energy of row y-1, completed at the next step
+#pragma unroll
+            for (int v = 0; v < VPL; ++v) { Ppend.q[v] = add4(Xin.q[v], tn.q[v]); Dpend.q[v] = Din.q[v]; }
+            if (label_row != nullptr) label_row += g.W;
+        }
         row_off += row_stride;
     };
 
@@ -411,6 +448,9 @@ __device__ __forceinline__ void tmast_task(const CUtensorMap *tmW, const CUtenso
     tma_store_fence();
     if (tid == 0) tma_store_wait_read();
     __syncthreads();
+    if (READOUT) {                             // row yb1: its E' was staged by the last step
+        if (label_row != nullptr && px >= 1) emit_label((yb1 + 1 - yb0) & 1);
+    }
     if (tid == 0) {
         const int last_par = (yb1 + 1 - yb0) & 1;
         tma_store_row(tsN, PUSH ? pmaps->N : nullptr, 1, last_par, yb1);

@@ -37,6 +37,8 @@ int launch_tmast(hsm_matcher *m, bool store_s, bool *launched)
     IterArgs a = iter_args(m, strips, store_s, ((NT == 256) ? (VPL == 1 ? 3 : 2) : (VPL == 1 ? 2 : 1)));
     const int bands = (m->ohi - m->olo + 1 + a.band_rows - 1) / a.band_rows;
     dim3 grid(strips, bands, m->launch_frames);
+    a.labels = store_s ? m->labels : nullptr;            // the finalising launch also writes the argmin labels
+    m->labels_fused = store_s;
     const bool full = (m->D == 4 * LPP * VPL);
     const int in = m->cur, out = m->cur ^ 1;
     PushMaps pmaps;

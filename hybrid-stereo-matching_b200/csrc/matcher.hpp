@@ -129,6 +129,10 @@ struct hsm_matcher {
     // first iteration then reads no plane at all (zero-filled by the TMA unit), and whoever needs real zeros in
     // memory (read-backs, the alternative kernels, n_iter = 0) materialises them first.
     bool zero_messages = false;
+    // the finalising launch of the default kernel also wrote the argmin labels of the batch into `labels`
+    // (fused readout): hsm_readout only has to copy them
+    bool labels_valid = false;
+    bool labels_fused = false;                   // set by the launch code when the last launch carried the readout
     int vlo = 0, vhi = 0, olo = 0, ohi = 0;
     // row-band mode with peer-to-peer halo push (hsm_peer_*): side 0 = band above, 1 = band below
     struct Peer {

@@ -42,12 +42,28 @@ def next_n_iter(n_iter, last_duration_ms, frame_budget_ms, min_iter=1, max_iter=
     return min(max_iter, max(min_iter, n_iter))
 
 
+def default_capacity(rows, cols, n_levels, n_frames=None, budget_bytes=6 << 30, most=64):
+    """Frames per launch for a matcher of this geometry: as many as fit a device-memory budget per lane (the arena
+    holds 8 planes per frame: 44 MB at 240x180xD32, 630 MB at 640x480xD64, 17 GB at 1920x1080xD256), at most
+    ``most`` and no more than the sequence has.  No CUDA call (the object may be built before a fork)."""
+    import ctypes
+    from . import _capi
+    one = ctypes.c_size_t()
+    _capi.check(_capi.lib().hsm_device_bytes(int(rows), int(cols), int(n_levels), 1, ctypes.byref(one)))
+    capacity = max(1, min(int(most), int(budget_bytes // max(one.value, 1))))
+    if n_frames is not None:
+        capacity = max(1, min(capacity, int(n_frames)))
+    return capacity
+
+
 class FramebasedStereoMatching(object):
-    def __init__(self, resolution, max_disparity, algorithm="mrf", inputs=None, capacity=64, device=0,
+    def __init__(self, resolution, max_disparity, algorithm="mrf", inputs=None, capacity=None, device=0,
                  matcher_factory=None):
         if algorithm == "mrf":
             # (x, y) resolution -> numpy (rows, cols) = (y, x)            stereo_framebased.py:18-21
             x, y = resolution
+            if capacity is None and matcher_factory is None:
+                capacity = default_capacity(y, x, max_disparity, None if inputs is None else len(inputs["ts"]))
             factory = matcher_factory or (lambda dim, levels: StereoMRF(dim, levels, capacity=capacity, device=device))
             self.algorithm = factory((y, x), max_disparity)
             if inputs is not None:

@@ -13,11 +13,15 @@ Differences that are deliberate and invisible to the reference's callers:
   * extra, optional surface: ``capacity`` (frames per launch) and ``lbp_batch``.
 """
 import ctypes
+import logging
+import time
 import weakref
 
 import numpy as np
 
 from . import _capi
+
+logger = logging.getLogger(__name__)
 
 _IMAGE_CODES = {np.dtype(np.float32): _capi.F32, np.dtype(np.float64): _capi.F64}
 _PRIOR_CODES = {np.dtype(np.float32): _capi.F32, np.dtype(np.float64): _capi.F64,
@@ -182,8 +186,22 @@ class StereoMRF(object):
         n_frames, keep_alive, args = self._host_inputs(image_left, image_right, prior, prior_trust_factor,
                                                        prior_influence_mode, _batched)
         _capi.check(_capi.lib().hsm_init_fields(*args, 1 if reinit_messages else 0, 0))
+        self._remember_images(keep_alive[0], keep_alive[1])
         del keep_alive
         self._frames, self._batched = n_frames, _batched
+
+    def _remember_images(self, image_left, image_right):
+        """``reference_image`` / ``secondary_image`` of mrf.py:41-42 (float32 casts of the last pair), built when
+        somebody reads them."""
+        self._last_pair = (image_left, image_right)
+
+    @property
+    def reference_image(self):
+        return np.asarray(self._last_pair[0]).astype("float32")
+
+    @property
+    def secondary_image(self):
+        return np.asarray(self._last_pair[1]).astype("float32")
 
     def _update_message_fields(self):
         """One iteration: south, west, north, east sweeps (mrf.py:73-94)."""
@@ -194,7 +212,11 @@ class StereoMRF(object):
         """Initialise the fields and run ``n_iter`` iterations (mrf.py:106-134)."""
         self._init_fields(image_left, image_right, prior, prior_trust_factor,
                           prior_influence_mode, reinit_messages=reinit_messages)
+        start = time.time()
         _capi.check(_capi.lib().hsm_iterate(self._handle, int(n_iter), 1))
+        if logger.isEnabledFor(logging.DEBUG):                           # mrf.py:134 (needs the device to finish)
+            self.synchronize()
+            logger.debug("Mean iteration time: %ss", (time.time() - start) / max(int(n_iter), 1))
 
     def _readout(self):
         if self._frames == 0:
@@ -220,7 +242,10 @@ class StereoMRF(object):
         n_frames, keep_alive, args = self._host_inputs(image_left, image_right, prior, prior_trust_factor,
                                                        prior_influence_mode, False)
         labels = np.empty((1, self._rows, self._cols), dtype=np.int64)
+        start = time.time()
         _capi.check(_capi.lib().hsm_lbp(*args, int(n_iter), labels.ctypes.data_as(ctypes.c_void_p), 0, 0))
+        logger.debug("Mean iteration time: %ss", (time.time() - start) / max(int(n_iter), 1))      # mrf.py:134
+        self._remember_images(keep_alive[0], keep_alive[1])
         del keep_alive
         self._frames, self._batched = n_frames, False
         self._belief_field_cache = labels[0]

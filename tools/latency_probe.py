@@ -6,7 +6,7 @@ import hybrid_stereo_matching_b200 as hsm
 from importlib import import_module
 synth = import_module("hybrid-stereo-matching_b200.synth")
 capi = import_module("hybrid-stereo-matching_b200._capi")
-for (rows, cols, levels, n_iter) in [(180, 240, 32, 50), (180, 240, 32, 10), (60, 80, 22, 10), (288, 384, 15, 10), (480, 640, 64, 100)]:
+for (rows, cols, levels, n_iter) in [(480, 640, 64, 100), (180, 240, 32, 50), (180, 240, 32, 10), (60, 80, 22, 10), (288, 384, 15, 10)]:
     l, r, d = synth.textured_pair(rows, cols, levels, 5)
     p = synth.sparse_prior(d, levels, 5)
     m = hsm.StereoMRF((rows, cols), levels)
