@@ -24,6 +24,7 @@ PRIOR_NONE, PRIOR_CONST, PRIOR_ADAPTIVE, PRIOR_CONST_F64 = 0, 1, 2, 3
 OPT_ALGORITHM, OPT_BAND_ROWS, OPT_DATA_TERM = 0, 1, 2
 OPT_VALID_LO, OPT_VALID_HI, OPT_OUT_LO, OPT_OUT_HI, OPT_STAGES, OPT_LANE_CONFIG = 3, 4, 5, 6, 7, 8
 OPT_FRAME_GROUPS = 9
+OPT_WAVE_FRAMES = 10
 PLANES = ("south", "west", "north", "east", "data")      # reference dict order, mrf.py:15-19
 
 
@@ -156,6 +157,7 @@ def lib():
         "hsm_rasterise_events": ([sz, vp, vp, vp, vp, ci, vp, vp, ci, ci, ci, cd, vp, vp, ci], ci),
         "hsm_rescale_frames": ([ci, ci, ci, vp, ci, ci, vp, ci], ci),
         "hsm_adjust_priors": ([ci, ci, ci, vp, cd, ci, vp, ci], ci),
+        "hsm_fit_velocity_field": ([sz, vp, vp, vp, cd, cd, cd, cd, cd, ci, ci, vp, ci], ci),
         "hsm_device_alloc": ([sz, ci, ctypes.POINTER(vp)], ci),
         "hsm_device_free": ([vp, ci], ci),
         "hsm_device_read": ([vp, vp, sz, ci], ci),

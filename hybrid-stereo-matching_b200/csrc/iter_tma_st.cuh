@@ -309,11 +309,14 @@ __device__ __forceinline__ void tmast_task(const CUtensorMap *tmW, const CUtenso
     if (READOUT && a.labels != nullptr)
         label_row = a.labels + ((size_t)frame * g.H + (size_t)(yb0 - 2)) * g.W + x;     // row of step yb0's (absent) label
     // label of the pixel whose partial energy is pending: E' from staging buffer `buf`, slot of column x
+    // (called by EVERY thread of the CTA: the argmin exchanges values with full-warp shuffles; a lane whose pixel
+    // is not owned -- the halo column px = 0 has no slot to its left -- reads its own slot and stores nothing)
+    const int e_back = px >= 1 ? g.Dp / 4 : 0;
     auto emit_label = [&](int buf) {
         Vec<VPL> en;
 #pragma unroll
         for (int v = 0; v < VPL; ++v) {
-            const float4 e4 = (FULL || ln.active[v]) ? st_ep[buf * ost_f4 + v * LPP - (g.Dp / 4)] : zero4();
+            const float4 e4 = (FULL || ln.active[v]) ? st_ep[buf * ost_f4 + v * LPP - e_back] : zero4();
             en.q[v] = add4(add4(Ppend.q[v], e4), Dpend.q[v]);
         }
         float best;
@@ -389,7 +392,7 @@ __device__ __forceinline__ void tmast_task(const CUtensorMap *tmW, const CUtenso
         }
         if (++stage == stages) { stage = 0; phase ^= 1u; }
         if (READOUT) {                         // row y-2: its E' was staged at the previous step (buffer par ^ 1)
-            if (label_row != nullptr && y >= yb0 + 2 && px >= 1) emit_label(par ^ 1);
+            if (label_row != nullptr && y >= yb0 + 2) emit_label(par ^ 1);      // (CTA-uniform condition)
         }
         // X = S'(y, x) + W'(y, x)
 #pragma unroll
@@ -449,7 +452,7 @@ __device__ __forceinline__ void tmast_task(const CUtensorMap *tmW, const CUtenso
     if (tid == 0) tma_store_wait_read();
     __syncthreads();
     if (READOUT) {                             // row yb1: its E' was staged by the last step
-        if (label_row != nullptr && px >= 1) emit_label((yb1 + 1 - yb0) & 1);
+        if (label_row != nullptr) emit_label((yb1 + 1 - yb0) & 1);
     }
     if (tid == 0) {
         const int last_par = (yb1 + 1 - yb0) & 1;

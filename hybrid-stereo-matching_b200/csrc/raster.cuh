@@ -16,6 +16,7 @@
 #pragma once
 
 #include <cuda_runtime.h>
+#include <math_constants.h>
 #include <stdint.h>
 
 namespace hsm {
@@ -261,6 +262,158 @@ static __global__ void k_adjust_priors(const double *__restrict__ prior, float *
             }
         }
         out[i] = (float)value;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Event-based visual flow (row N4): VelocityVectorField._fit_velocity_field, stereovis/spiking/algorithms/vvf.py:32-82
+// (Benosman et al. 2014 as the reference implements it).  Events (t, x, y) of one polarity, sorted by time.  For
+// every event: the candidates are the events with  t_e - dt < t <= t_e + dt  (the two np.searchsorted(side='right')
+// of vvf.py:46-47) inside the (2 nx + 1) x (2 ny + 1) pixel neighbourhood; with fewer than `min_events` of them the
+// velocity stays 0; otherwise a plane  t ~ a x + b y + c  is fitted by least squares and refined at most
+// `max_iter` times: keep the candidates with |(t, x, y) . n| <= rejection_threshold for n = (c, a, b) / |(c, a, b)|
+// (the reference's expression, vvf.py:66-69, as written), stop if fewer than `min_events` or all of them remain,
+// refit on the kept ones, stop when the parameters move by less than `convergence_threshold`.  Result: (a, b).
+// The reference solves each fit with scipy.linalg.lstsq (LAPACK gelsd, an SVD); here the 3 x 3 normal equations
+// are accumulated in float64 with coordinates taken relative to the event (so the sums stay small and the
+// solution matches the SVD's to ~1e-9 relative for the well-posed neighbourhoods) and solved by Cramer's rule;
+// collinear neighbourhoods (an edge's events all in one pixel column) get the minimum-norm solution, as an
+// SVD-based lstsq returns it, from an eigen-decomposition of the normal matrix (min_norm_solve3).
+// One thread per event; every refit is another pass over the event's time window.
+// ---------------------------------------------------------------------------
+// Minimum-norm least-squares solution of the 3 x 3 normal equations M p = b for a (numerically) singular M, via
+// a cyclic Jacobi eigen-decomposition: p = sum over eigenvalues above the threshold of (v . b / lambda) v -- what
+// an SVD-based lstsq returns for a rank-deficient system (collinear neighbourhoods: e.g. an edge's events all in
+// one pixel column).
+__device__ __forceinline__ void min_norm_solve3(const double m_in[6], const double b[3], double p[3])
+{
+    // m_in = {m00, m01, m02, m11, m12, m22}
+    double a[3][3] = {{m_in[0], m_in[1], m_in[2]}, {m_in[1], m_in[3], m_in[4]}, {m_in[2], m_in[4], m_in[5]}};
+    double v[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+    for (int sweep = 0; sweep < 12; ++sweep) {
+        const double off = fabs(a[0][1]) + fabs(a[0][2]) + fabs(a[1][2]);
+        if (off == 0.0) break;
+        for (int pi = 0; pi < 2; ++pi) {
+            for (int qi = pi + 1; qi < 3; ++qi) {
+                if (a[pi][qi] == 0.0) continue;
+                const double theta = (a[qi][qi] - a[pi][pi]) / (2.0 * a[pi][qi]);
+                const double tt = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                const double c = 1.0 / sqrt(tt * tt + 1.0), sn = tt * c;
+                for (int k = 0; k < 3; ++k) {                 // A <- A J
+                    const double akp = a[k][pi], akq = a[k][qi];
+                    a[k][pi] = c * akp - sn * akq;
+                    a[k][qi] = sn * akp + c * akq;
+                }
+                for (int k = 0; k < 3; ++k) {                 // A <- J^T A
+                    const double apk = a[pi][k], aqk = a[qi][k];
+                    a[pi][k] = c * apk - sn * aqk;
+                    a[qi][k] = sn * apk + c * aqk;
+                }
+                for (int k = 0; k < 3; ++k) {                 // V <- V J
+                    const double vkp = v[k][pi], vkq = v[k][qi];
+                    v[k][pi] = c * vkp - sn * vkq;
+                    v[k][qi] = sn * vkp + c * vkq;
+                }
+            }
+        }
+    }
+    const double lmax = fmax(fmax(fabs(a[0][0]), fabs(a[1][1])), fabs(a[2][2]));
+    p[0] = p[1] = p[2] = 0.0;
+    for (int i = 0; i < 3; ++i) {
+        const double lambda = a[i][i];
+        if (!(lambda > 1e-13 * lmax)) continue;
+        const double w = (v[0][i] * b[0] + v[1][i] * b[1] + v[2][i] * b[2]) / lambda;
+        p[0] += w * v[0][i]; p[1] += w * v[1][i]; p[2] += w * v[2][i];
+    }
+}
+
+struct FlowFitArgs {
+    const double *t, *x, *y;
+    size_t n;
+    double dt, nx, ny, rejection, convergence;
+    int max_iter, min_events;
+};
+
+static __global__ void k_vvf_fit(FlowFitArgs a, double *__restrict__ vel)
+{
+    for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < a.n; e += (size_t)gridDim.x * blockDim.x) {
+        const double te = a.t[e], xe = a.x[e], ye = a.y[e];
+        double va = 0.0, vb = 0.0;
+        // window [lo, hi): first index with t > te - dt, first index with t > te + dt
+        size_t lo, hi;
+        {
+            size_t l = 0, h = a.n;
+            const double key = te - a.dt;
+            while (l < h) { const size_t m = (l + h) >> 1; if (a.t[m] <= key) l = m + 1; else h = m; }
+            lo = l;
+            l = lo; h = a.n;
+            const double key2 = te + a.dt;
+            while (l < h) { const size_t m = (l + h) >> 1; if (a.t[m] <= key2) l = m + 1; else h = m; }
+            hi = l;
+        }
+        // parameters of the current plane in absolute coordinates (a, b, c); `use_plane` = refit with rejection
+        double pa = 0.0, pb = 0.0, pc = 0.0;
+        bool have = false;
+        long n_candidates = 0;
+        for (int pass = 0; pass <= a.max_iter; ++pass) {
+            double nrm = 0.0, na = 0.0, nb = 0.0, nc = 0.0;
+            if (have) {
+                nrm = sqrt(pc * pc + pa * pa + pb * pb);
+                nc = pc / nrm; na = pa / nrm; nb = pb / nrm;
+            }
+            double sxx = 0, sxy = 0, syy = 0, sx = 0, sy = 0, sxt = 0, syt = 0, st = 0;
+            long cnt = 0;
+            for (size_t j = lo; j < hi; ++j) {
+                const double xj = a.x[j], yj = a.y[j];
+                if (!(fabs(xj - xe) <= a.nx && fabs(yj - ye) <= a.ny)) continue;
+                const double tj = a.t[j];
+                if (have && !(fabs(tj * nc + xj * na + yj * nb) <= a.rejection)) continue;
+                const double dx = xj - xe, dy = yj - ye, dtj = tj - te;
+                sxx += dx * dx; sxy += dx * dy; syy += dy * dy; sx += dx; sy += dy;
+                sxt += dx * dtj; syt += dy * dtj; st += dtj;
+                ++cnt;
+            }
+            if (!have) {
+                n_candidates = cnt;
+                if (cnt < a.min_events) break;                       // velocity stays 0 (vvf.py:53-55)
+            } else if (cnt < a.min_events || cnt == n_candidates) {
+                break;                                               // keep the parameters found so far
+            }
+            // normal equations in event-relative coordinates: [sxx sxy sx; sxy syy sy; sx sy n] p = [sxt syt st]
+            const double n = (double)cnt;
+            const double det = sxx * (syy * n - sy * sy) - sxy * (sxy * n - sy * sx) + sx * (sxy * sy - syy * sx);
+            const double scale = (sxx + syy + n);
+            double qa, qb, qc;
+            if (fabs(det) > 1e-12 * scale * scale * scale) {
+                qa = (sxt * (syy * n - sy * sy) - sxy * (syt * n - sy * st) + sx * (syt * sy - syy * st)) / det;
+                qb = (sxx * (syt * n - st * sy) - sxt * (sxy * n - sy * sx) + sx * (sxy * st - syt * sx)) / det;
+                const double qc_rel =
+                    (sxx * (syy * st - sy * syt) - sxy * (sxy * st - syt * sx) + sxt * (sxy * sy - syy * sx)) / det;
+                qc = qc_rel + te - qa * xe - qb * ye;                // back to absolute coordinates
+            } else {
+                // collinear neighbourhood: the minimum-norm solution in ABSOLUTE coordinates (it is not
+                // translation invariant); absolute sums from the event-relative ones
+                const double X = sx + n * xe, Y = sy + n * ye, T = st + n * te;
+                const double m[6] = {sxx + 2.0 * xe * sx + n * xe * xe, sxy + xe * sy + ye * sx + n * xe * ye, X,
+                                     syy + 2.0 * ye * sy + n * ye * ye, Y, n};
+                const double rhs[3] = {sxt + xe * st + te * sx + n * xe * te, syt + ye * st + te * sy + n * ye * te, T};
+                double p[3];
+                min_norm_solve3(m, rhs, p);
+                qa = p[0]; qb = p[1]; qc = p[2];
+            }
+            if (have) {
+                const double da = pa - qa, db = pb - qb, dc = pc - qc;
+                const double eps = sqrt(da * da + db * db + dc * dc);
+                pa = qa; pb = qb; pc = qc;
+                if (!(eps > a.convergence)) break;
+            } else {
+                pa = qa; pb = qb; pc = qc;
+                have = true;
+            }
+        }
+        if (have) { va = pa; vb = pb; }
+        vel[2 * e] = va;
+        vel[2 * e + 1] = vb;
     }
 }
 

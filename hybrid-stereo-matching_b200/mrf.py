@@ -172,6 +172,9 @@ class StereoMRF(object):
             left, right = left.astype("float32"), right.astype("float32")
             code = _capi.F32
         mode, keep32, keep64 = _blend(prior, prior_trust_factor, prior_influence_mode)
+        if mode == _capi.PRIOR_ADAPTIVE and self.n_levels > self._cols:
+            # level l = cols slices an empty column range and the reference's data_diff.max() raises (mrf.py:59)
+            raise ValueError("zero-size array to reduction operation maximum which has no identity")
         prior_ptr, prior_code = None, _capi.F32
         if prior is not None:
             prior, prior_code = _as_prior(prior)

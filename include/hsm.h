@@ -75,6 +75,11 @@ extern "C" {
 #define HSM_OPT_FRAME_GROUPS 9 /* 2 = launch every iteration as two kernels (halves of the frames) on two streams so
                                   that each fills the other's tail; 1 = one kernel; 0 = automatic (2 whenever there are >= 2 frames) */
 
+#define HSM_OPT_WAVE_FRAMES 10 /* batches: k > 0 = every stream takes k frames through ALL iterations before it moves on
+                                  to the next k (a "wave"), so that the messages of the frames in flight stay in the
+                                  126 MB L2 instead of streaming through HBM once per iteration; -1 = one launch per
+                                  iteration over the whole batch half (HBM-streaming schedule); 0 = automatic        */
+
 typedef struct hsm_matcher hsm_matcher;
 
 typedef struct hsm_stats {
@@ -246,6 +251,19 @@ int hsm_rescale_frames(int n_frames, int rows, int cols, const double *in, int o
  */
 int hsm_adjust_priors(int n_frames, int rows, int cols, const double *prior, double nondata, int time_arrow, float *out,
                       int device);
+
+/*
+ * Event-based visual flow (next row N4): replaces VelocityVectorField._fit_velocity_field
+ * (stereovis/spiking/algorithms/vvf.py:32-82) for ONE polarity group: events sorted by time, host arrays t, x, y
+ * of n_events float64; velocities: n_events x 2 float64 (x, y slope of the fitted time plane; 0 where the
+ * neighbourhood has fewer than min_events events; the minimum-norm solution where it is collinear).  float64
+ * throughout; agreement
+ * with the reference's SVD-based least squares is to rounding (~1e-9 relative), not bit for bit.
+ */
+int hsm_fit_velocity_field(size_t n_events, const double *t, const double *x, const double *y, double time_interval,
+                           double neighbourhood_x, double neighbourhood_y, double rejection_threshold,
+                           double convergence_threshold, int max_iter_steps, int min_events, double *velocities,
+                           int device);
 
 /*
  * Self-test of the shared-reciprocal division used by the fused kernel: a4 holds n x 4

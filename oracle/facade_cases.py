@@ -47,6 +47,35 @@ ADJUST_CASES = [
 ]
 
 
+# VelocityVectorField.fit_velocity_field (vvf.py:84-110): moving edges (so that planes fit and the rejection loop
+# runs) plus background noise events; unique pixel/time jitter keeps the neighbourhoods well-posed
+FLOW_CASES = [
+    dict(name="v01_edge_moving_right", seed=31, res=(40, 30), speed=(0.05, 0.0), n_noise=150, t_max=400.0, dt=20),
+    dict(name="v02_edge_moving_diagonally", seed=32, res=(40, 30), speed=(0.04, 0.03), n_noise=300, t_max=400.0, dt=50),
+    dict(name="v03_sparse_noise_only", seed=33, res=(30, 20), speed=None, n_noise=400, t_max=300.0, dt=20),
+]
+
+
+def flow_events(case):
+    """(N, 4) events (t, x, y, polarity), unsorted: an edge sweeping across the frame + uniform noise."""
+    rng = np.random.default_rng(case["seed"])
+    cols, rows = case["res"]
+    events = []
+    if case["speed"] is not None:
+        vx, vy = case["speed"]                        # pixels per ms
+        for t in np.arange(0.0, case["t_max"], 1.0):
+            for y in range(rows):
+                x = vx * t + (vy * t) * 0.0 + 0.15 * y * (1.0 if vy else 0.0)
+                xi = int(np.floor(x + vy * t)) % cols
+                if rng.random() < 0.6:
+                    events.append((t + rng.random() * 0.9, float(xi), float(y), float(rng.integers(0, 2))))
+    n = case["n_noise"]
+    noise = np.stack([rng.random(n) * case["t_max"], rng.integers(0, cols, n).astype(float),
+                      rng.integers(0, rows, n).astype(float), rng.integers(0, 2, n).astype(float)], axis=1)
+    out = np.concatenate([np.asarray(events).reshape(-1, 4), noise], axis=0)
+    return out[rng.permutation(out.shape[0])]
+
+
 def adjust_inputs(case):
     """(reference_events (N, 4): t, x, y, polarity; prior frames (F, rows, cols) float64 with -1 = none)."""
     rng = np.random.default_rng(case["seed"])

@@ -61,3 +61,37 @@ def rescale(image, scale):
     if preserve:
         out[mask] = 0
     return out
+
+
+def fit_velocity_field(events, time_interval=20, neighbourhood_size=(3, 3), rejection_threshold=0.005,
+                       convergence_threshold=1e-5, max_iter_steps=5, min_events=10):
+    """vvf.py:32-82 restated for one polarity group: ``events`` (N, 3) of (t, x, y) sorted by time -> (N, 2).
+    Least squares through numpy's lstsq (an SVD like the reference's scipy.linalg.lstsq)."""
+    events = np.asarray(events, dtype=np.float64)
+    velocities = np.zeros((events.shape[0], 2))
+    times_all = events[:, 0]
+    for index, event in enumerate(events):
+        first = np.searchsorted(times_all, event[0] - time_interval, side="right")
+        last = np.searchsorted(times_all, event[0] + time_interval, side="right")
+        window = events[first:last]
+        near = window[(np.abs(window[:, 1] - event[1]) <= neighbourhood_size[0])
+                      & (np.abs(window[:, 2] - event[2]) <= neighbourhood_size[1])]
+        count = near.shape[0]
+        if count < min_events:
+            continue
+        positions = np.hstack([near[:, 1:], np.ones((count, 1))])
+        times = near[:, 0]
+        best = np.linalg.lstsq(positions, times, rcond=None)[0]
+        epsilon, steps = np.inf, 0
+        while steps < max_iter_steps and epsilon > convergence_threshold:
+            steps += 1
+            normal = np.hstack((best[2], best[:-1]))
+            normal = normal / np.linalg.norm(normal)
+            accepted = np.where(np.abs(np.dot(near, normal)) <= rejection_threshold)[0]
+            if accepted.size < min_events or accepted.size == count:
+                break
+            new = np.linalg.lstsq(positions[accepted], times[accepted], rcond=None)[0]
+            epsilon = np.linalg.norm(best - new)
+            best = new
+        velocities[index] = best[:-1]
+    return velocities

@@ -36,7 +36,15 @@ def main():
             arrays["stamps_%s" % fill] = np.asarray(stamps)
         np.savez_compressed(F.fixture_path(case), **arrays)
         print("%-36s %s" % (case["name"], arrays["frames_-1"].shape), flush=True)
-    _, correction_class = flow_ref.load()
+    field_class, correction_class = flow_ref.load()
+    for case in F.FLOW_CASES:
+        events = F.flow_events(case)
+        field = field_class(time_interval=case["dt"], neighbourhood_size=(3, 3), rejection_threshold=0.005,
+                            convergence_threshold=1e-5, max_iter_steps=5, min_num_events_in_timespace_interval=10)
+        out = field.fit_velocity_field(events, assume_sorted=False, concatenate_polarity_groups=False)
+        np.savez_compressed(F.fixture_path(case), positive=out["positive"], negative=out["negative"])
+        fitted = int((out["positive"] != 0).any(axis=1).sum() + (out["negative"] != 0).any(axis=1).sum())
+        print("%-36s %d events, %d fitted" % (case["name"], events.shape[0], fitted), flush=True)
     for case in F.ADJUST_CASES:
         events, frames = F.adjust_inputs(case)
         correction = correction_class(case["res"], events, buffer_pivots=case["pivots"],

@@ -99,3 +99,46 @@ def test_prepare_frames_full_pipeline(hsm):
     for i in range(2):
         small = flow_numpy.rescale(frames[i][25:145, 55:195], 0.5)
         assert got[i].tobytes() == frames_numpy.normalise_contrast(small).tobytes()
+
+
+# ---- velocity field (vvf.py) ---------------------------------------------------------------------------
+FLOW_IDS = [c["name"] for c in F.FLOW_CASES]
+
+
+def _polarity_groups(events):
+    events = events[np.argsort(events[:, 0], kind="stable")]
+    positive = events[:, 3] == 0
+    return events[positive][:, :-1], events[~positive][:, :-1]
+
+
+@pytest.mark.parametrize("case", F.FLOW_CASES[:1] + F.FLOW_CASES[2:], ids=[FLOW_IDS[0], FLOW_IDS[2]])
+def test_numpy_velocity_field_matches_reference_fixture(case):
+    """The restatement against the REAL VelocityVectorField's output (float64, SVD least squares on both sides)."""
+    data = np.load(F.fixture_path(case), allow_pickle=False)
+    positive, negative = _polarity_groups(F.flow_events(case))
+    for group, want in ((positive, data["positive"]), (negative, data["negative"])):
+        group = group[:1500]                                   # the CPU suite's time budget
+        got = flow_numpy.fit_velocity_field(group, time_interval=case["dt"])
+        # a prefix of the stream sees the same neighbourhoods except within dt of its end
+        keep = group[:, 0] < group[-1, 0] - case["dt"] if group.shape[0] else np.zeros(0, dtype=bool)
+        assert np.allclose(got[keep], want[:group.shape[0]][keep], rtol=1e-9, atol=1e-12)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", F.FLOW_CASES, ids=FLOW_IDS)
+def test_cuda_velocity_field_matches_reference_fixture(hsm, case):
+    """float64 plane fits on the GPU (normal equations) vs the reference's scipy lstsq: equal to rounding.
+    Tolerance: 1e-6 relative + 1e-9 absolute on each velocity component."""
+    from importlib import import_module
+    flow = import_module("hybrid-stereo-matching_b200.flow")
+    data = np.load(F.fixture_path(case), allow_pickle=False)
+    field = flow.VelocityVectorField(time_interval=case["dt"])
+    got = field.fit_velocity_field(F.flow_events(case), assume_sorted=False, concatenate_polarity_groups=False)
+    for name in ("positive", "negative"):
+        want = data[name]
+        assert got[name].shape == want.shape
+        assert np.isfinite(got[name]).all()
+        assert np.array_equal((np.abs(got[name]) > 1e-9).any(axis=1), (np.abs(want) > 1e-9).any(axis=1))
+        assert np.allclose(got[name], want, rtol=1e-6, atol=1e-9), float(np.abs(got[name] - want).max())
+    stacked = field.fit_velocity_field(F.flow_events(case))
+    assert stacked.shape == (data["positive"].shape[0] + data["negative"].shape[0], 2)

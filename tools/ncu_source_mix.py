@@ -2,7 +2,8 @@
 import csv, re, sys
 rows = list(csv.reader(open(sys.argv[1])))
 steps = float(sys.argv[2]) if len(sys.argv) > 2 else 1.0
-hdr, data = rows[1], rows[2:]
+hdr = rows[1]
+data = [r for r in rows[2:] if len(r) == len(hdr)]
 ia, ie, iss = hdr.index('Source'), hdr.index('Instructions Executed'), hdr.index('Warp Stall Sampling (All Samples)')
 tot = sum(int(r[ie]) for r in data); totS = sum(int(r[iss]) for r in data)
 print("total warp instructions", tot, "per step %.1f" % (tot / steps), "samples", totS)
