@@ -24,7 +24,6 @@ PRIOR_NONE, PRIOR_CONST, PRIOR_ADAPTIVE, PRIOR_CONST_F64 = 0, 1, 2, 3
 OPT_ALGORITHM, OPT_BAND_ROWS, OPT_DATA_TERM = 0, 1, 2
 OPT_VALID_LO, OPT_VALID_HI, OPT_OUT_LO, OPT_OUT_HI, OPT_STAGES, OPT_LANE_CONFIG = 3, 4, 5, 6, 7, 8
 OPT_FRAME_GROUPS = 9
-OPT_WAVE_FRAMES = 10
 PLANES = ("south", "west", "north", "east", "data")      # reference dict order, mrf.py:15-19
 
 

@@ -294,13 +294,13 @@ int choose_band_rows(const hsm_matcher *m, int strips, int ctas_per_sm)
     // beyond ~64 rows the halo saving is below 3 % and taller bands only lengthen the drain.
     // Bands are normally at least 12 rows; when even 12-row bands cannot fill the machine once (a single
     // small frame: latency-, not bandwidth-bound) they may shrink to 4 rows.
-    const long per_band = (long)strips * (m->sched_frames > 0 ? m->sched_frames : m->frames);
+    const long per_band = (long)strips * m->frames;
     int min_rows = 12;
     while (min_rows > 4 && per_band * ((rows + min_rows - 1) / min_rows) < (long)m->sm_count * 3) min_rows -= 2;
     // a tiny single frame (the shipped 80x60 configurations): not even one CTA per SM at 4 rows, and an iteration
     // is the latency of one band -- 2-row bands measured 6.4 us per iteration against 8.7 at 4 rows
     if (min_rows == 4 && per_band * ((rows + 3) / 4) < (long)m->sm_count) min_rows = 2;
-    const bool grouped = m->launch_frames < m->frames && m->sched_frames == 0;
+    const bool grouped = m->launch_frames < m->frames;
     const long target = (long)m->sm_count * std::max(1, ctas_per_sm) * (grouped ? 4 : 6);
     long bands = std::max((target + per_band - 1) / per_band, (long)(rows + 63) / 64);
     bands = std::max(1L, std::min<long>(bands, std::max(1, rows / min_rows)));
@@ -705,9 +705,6 @@ int hsm_set_option(hsm_matcher *m, int key, int value)
         case HSM_OPT_FRAME_GROUPS:
             if (value < 0 || value > 2) return fail(HSM_ERR_ARG, "frame groups must be 0 (auto), 1 or 2");
             m->frame_groups = value; return HSM_OK;
-        case HSM_OPT_WAVE_FRAMES:
-            if (value < -1 || value > 65535) return fail(HSM_ERR_ARG, "wave frames must be -1 (off), 0 (auto) or a frame count");
-            m->wave_frames = value; return HSM_OK;
         default: return fail(HSM_ERR_ARG, "unknown option %d", key);
     }
 }
@@ -726,7 +723,6 @@ int hsm_get_option(hsm_matcher *m, int key, int *value)
         case HSM_OPT_STAGES: *value = m->stages; return HSM_OK;
         case HSM_OPT_LANE_CONFIG: *value = m->lane_config; return HSM_OK;
         case HSM_OPT_FRAME_GROUPS: *value = m->frame_groups; return HSM_OK;
-        case HSM_OPT_WAVE_FRAMES: *value = m->wave_frames; return HSM_OK;
         default: return fail(HSM_ERR_ARG, "unknown option %d", key);
     }
 }
@@ -863,52 +859,6 @@ int hsm_iterate(hsm_matcher *m, int n_iter, int finalize)
     }
     const int n_groups = grouped ? 2 : 1;
     m->labels_fused = false;
-    // Wave schedule (HSM_OPT_WAVE_FRAMES): each of the two streams takes a few frames through ALL iterations, then
-    // the next few.  The W / N / E planes of the frames in flight (24 B x H x W x Dp each, both generations) then
-    // stay in L2 from one iteration to the next: HBM sees each frame's state about once instead of once per
-    // iteration.  Same kernels, same bits -- only the order of the launches changes.
-    int wave = m->wave_frames;
-    if (wave == 0) wave = -1;                                  // automatic: off until measured otherwise
-    if (grouped && wave > 0 && m->algorithm == 5 && tma_supported(m) && n_iter >= 2) {
-        static const bool pdl_on = getenv("HSM_NO_PDL") == nullptr;
-        const int half = (m->frames + 1) / 2;
-        const int cur0 = m->cur;
-        const bool zero0 = m->zero_messages;
-        const int waves = (half + wave - 1) / wave;
-        m->sched_frames = 2 * wave;
-        m->launch_pdl = pdl_on;
-        bool ok = true;
-        for (int w = 0; w < waves && ok; ++w) {
-            for (int group = 0; group < 2 && ok; ++group) {
-                const int f0 = (group == 0 ? 0 : half) + w * wave, f1 = group == 0 ? half : m->frames;
-                if (f0 >= f1) continue;
-                m->launch_frame0 = f0;
-                m->launch_frames = std::min(wave, f1 - f0);
-                m->launch_stream = group == 0 ? m->stream : m->aux_stream;
-                for (int it = 0; it < n_iter; ++it) {
-                    m->cur = cur0 ^ (it & 1);
-                    m->zero_messages = zero0 && it == 0;
-                    bool launched = false;
-                    HSM_TRY(launch_tmast_any(m, finalize && it == n_iter - 1, &launched));
-                    if (!launched) { ok = false; break; }            // (only possible at the very first launch)
-                }
-            }
-        }
-        m->sched_frames = 0;
-        m->launch_frame0 = 0; m->launch_frames = m->frames; m->launch_stream = m->stream;
-        m->zero_messages = ok ? false : zero0;
-        m->cur = ok ? (cur0 ^ (n_iter & 1)) : cur0;
-        if (ok) {
-            CUDA_TRY(cudaEventRecord(m->join_event, m->aux_stream));
-            CUDA_TRY(cudaStreamWaitEvent(m->stream, m->join_event, 0));
-            CUDA_TRY(cudaEventRecord(ev.second, m->stream));
-            m->pending.push_back(ev);
-            m->stats.iterations += (uint64_t)n_iter;
-            m->s_valid = finalize != 0;
-            m->labels_valid = finalize != 0 && m->labels_fused;
-            return HSM_OK;
-        }
-    }
     // one kernel per iteration: let the next iteration's CTAs set up while this one drains (with frame
     // groups the other group's CTAs are the better use of those SMs; the peer-to-peer flags sit between
     // the kernels of a stream, so nothing is adjacent there)

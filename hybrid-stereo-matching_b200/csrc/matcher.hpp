@@ -155,8 +155,6 @@ struct hsm_matcher {
     // frames) on two streams, so that one group's tail (SMs idling while the last CTAs finish) is filled by
     // the other group's CTAs.  Set per launch by hsm_iterate; read by the launch_* functions.
     int frame_groups = 0;                        // HSM_OPT_FRAME_GROUPS: 0 = automatic, 1 = one launch per iteration
-    int wave_frames = 0;                         // HSM_OPT_WAVE_FRAMES
-    int sched_frames = 0;                        // frames in flight at a time (wave schedule), 0 = the whole batch
     int launch_frame0 = 0, launch_frames = 0;
     cudaStream_t launch_stream = nullptr, aux_stream = nullptr;
     unsigned *flow_state = nullptr;              // persistent dataflow kernel: task counter + per-tile progress

@@ -75,11 +75,6 @@ extern "C" {
 #define HSM_OPT_FRAME_GROUPS 9 /* 2 = launch every iteration as two kernels (halves of the frames) on two streams so
                                   that each fills the other's tail; 1 = one kernel; 0 = automatic (2 whenever there are >= 2 frames) */
 
-#define HSM_OPT_WAVE_FRAMES 10 /* batches: k > 0 = every stream takes k frames through ALL iterations before it moves on
-                                  to the next k (a "wave"), so that the messages of the frames in flight stay in the
-                                  126 MB L2 instead of streaming through HBM once per iteration; -1 = one launch per
-                                  iteration over the whole batch half (HBM-streaming schedule); 0 = automatic        */
-
 typedef struct hsm_matcher hsm_matcher;
 
 typedef struct hsm_stats {

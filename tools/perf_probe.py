@@ -28,7 +28,6 @@ def run(rows, cols, levels, batch, n_iter, algorithm, data_term, band_rows, stag
     m.set_option(capi.OPT_STAGES, stages)
     groups = int(os.environ.get("HSM_FRAME_GROUPS", "0"))
     m.set_option(capi.OPT_FRAME_GROUPS, groups)
-    m.set_option(capi.OPT_WAVE_FRAMES, int(os.environ.get("HSM_WAVE_FRAMES", "0")))
     m._init_fields(lefts, rights, priors, 1.0, "adaptive", True, _batched=True)
     capi.check(capi.lib().hsm_iterate(m._handle, int(os.environ.get("HSM_WARM", "3")), 1))
     m.synchronize()
@@ -40,8 +39,7 @@ def run(rows, cols, levels, batch, n_iter, algorithm, data_term, band_rows, stag
     hwd = rows * cols * levels
     algo_bytes = 24.0 * hwd * batch
     out = dict(shape="%dx%dxD%d" % (cols, rows, levels), batch=batch, algorithm=algorithm, data_term=data_term,
-               band_rows=band_rows, stages=stages, lane=lane, groups=groups,
-               wave=int(os.environ.get("HSM_WAVE_FRAMES", "0")), ms_per_iter=round(ms_iter, 4),
+               band_rows=band_rows, stages=stages, lane=lane, groups=groups, ms_per_iter=round(ms_iter, 4),
                eff_GBs=round(algo_bytes / ms_iter / 1e6, 1), frac=round(algo_bytes / ms_iter / 1e6 / PEAK, 3),
                frames_per_s_50it=round(batch / (ms_iter * 50 / 1e3), 1))
     print(json.dumps(out), flush=True)
