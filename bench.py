@@ -364,8 +364,8 @@ def band_legs(torch, dist, hsm, rank, world, local_rank, n_iter=50):
     # launch per GPU for the whole loop, boundary tiles exchange progress counters through peer memory; "nccl":
     # pack / send-recv / unpack after every iteration
     for exchange in ("p2p", "p2p_dataflow", "nccl"):
-        engine.matcher.set_option(capi.OPT_ALGORITHM, 6 if exchange == "p2p_dataflow" else 5)
-        matcher = bands.RowBandMatcher(engine, rank, world, exchange="nccl" if exchange == "nccl" else "p2p")
+        engine.matcher.set_option(capi.OPT_ALGORITHM, 5)
+        matcher = bands.RowBandMatcher(engine, rank, world, exchange=exchange)
         if exchange == "p2p_dataflow":
             matcher._attached = True                    # the neighbours are still attached from the "p2p" leg
         # parity first: the fixture's own call, gathered labels against the reference's
