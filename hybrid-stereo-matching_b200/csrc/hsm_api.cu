@@ -72,8 +72,11 @@ const LaneCfg kLaneTable[] = {{4, 1, 256}, {8, 1, 256}, {16, 1, 512}, {32, 1, 51
                               // entries 10..13: lanes-per-pixel counts that are not a power of two (default
                               // kernel family only): the reference's shipped disparity counts 20 and 22 are 5 and 6
                               // float4 chunks per pixel
-                              {5, 1, 256}, {6, 1, 256}, {5, 2, 256}, {6, 2, 256}};
-constexpr int kLaneTableSize = 13;
+                              {5, 1, 256}, {6, 1, 256}, {5, 2, 256}, {6, 2, 256},
+                              // entries 14..16: other CTA widths (7, 9, 10 warps = 42, 45, 40 pixels) for frames whose
+                              // width the 8-warp strips divide badly -- the shipped 80- and 70-column frames
+                              {5, 1, 224}, {6, 1, 288}, {8, 1, 320}};
+constexpr int kLaneTableSize = 16;
 
 bool is_pow2(int v) { return (v & (v - 1)) == 0; }
 
@@ -95,13 +98,26 @@ bool lane_cfg(int D, LaneCfg *c)
 
 // Lane layout of the default kernel family: the power-of-two choice unless 5 or 6 chunk slots per lane group
 // waste fewer lanes (D = 17..24 and 33..48; for 25..32 and 49..64 the 8-lane layouts are already as good).
-LaneCfg lane_cfg_st(int D, const LaneCfg &base)
+// pixel columns a frame of `cols` columns costs with this layout: strips x pixels per CTA (two of them halo)
+long strip_cost(const LaneCfg &c, int cols)
 {
-    if (D > 16 && D <= 20) return kLaneTable[9];
-    if (D > 20 && D <= 24) return kLaneTable[10];
-    if (D > 32 && D <= 40) return kLaneTable[11];
-    if (D > 40 && D <= 48) return kLaneTable[12];
-    return base;
+    const int px = (c.nt / 32) * (32 / c.lpp), tx = px - 2;
+    return (long)((cols + tx - 1) / tx) * px;
+}
+
+LaneCfg lane_cfg_st(int D, int cols, const LaneCfg &base)
+{
+    LaneCfg pick = base;
+    if (D > 16 && D <= 20) pick = kLaneTable[9];
+    else if (D > 20 && D <= 24) pick = kLaneTable[10];
+    else if (D > 32 && D <= 40) pick = kLaneTable[11];
+    else if (D > 40 && D <= 48) pick = kLaneTable[12];
+    // a CTA width that wastes fewer columns on this frame width, if there is one for the layout
+    for (int alt = 13; alt < kLaneTableSize; ++alt) {
+        const LaneCfg &c = kLaneTable[alt];
+        if (c.lpp == pick.lpp && c.vpl == pick.vpl && 10 * strip_cost(c, cols) < 9 * strip_cost(pick, cols)) pick = c;
+    }
+    return pick;
 }
 
 size_t plane_floats(const hsm_matcher *m) { return (size_t)m->cap * m->H * m->W * m->Dp; }
@@ -470,11 +486,12 @@ int ensure_maps(hsm_matcher *m)
             HSM_TRY(make_plane_map(m, &m->st.tsE[i], m->Em[i], px5 - 2));
         }
         HSM_TRY(make_plane_map(m, &m->st.tmD, m->Dt, px5));
-        const int dcov5 = 4 * m->cfg5.lpp * m->cfg5.vpl, rseg5 = px5 + dcov5 + 4;
+        const int px54 = (px5 + 3) / 4 * 4;                     // StageLayout::PX4
+        const int dcov5 = 4 * m->cfg5.lpp * m->cfg5.vpl, rseg5 = px54 + dcov5 + 4;
         const int rbox5 = rseg5 <= 256 ? rseg5 : ((rseg5 / 2 + 31) / 32 * 32);
-        HSM_TRY(make_image_map(m, &m->st.tmI.L, m->L, false, px5 + 4));
+        HSM_TRY(make_image_map(m, &m->st.tmI.L, m->L, false, px54 + 4));
         HSM_TRY(make_image_map(m, &m->st.tmI.R, m->R, false, rbox5));
-        HSM_TRY(make_image_map(m, &m->st.tmI.P, m->P, true, px5 + 4));
+        HSM_TRY(make_image_map(m, &m->st.tmI.P, m->P, true, px54 + 4));
         for (int side = 0; side < 2; ++side) {
             hsm_matcher::Peer &p = m->peer[side];
             if (!p.attached) continue;
@@ -621,7 +638,7 @@ int hsm_create(int rows, int cols, int n_levels, int capacity, int device, hsm_m
                     n_levels);
     hsm_matcher *m = new hsm_matcher();
     m->H = rows; m->W = cols; m->Wp = (cols + 3) / 4 * 4; m->D = n_levels; m->Dp = (n_levels + 3) / 4 * 4;
-    m->cap = capacity; m->device = device; m->cfg = cfg; m->cfg5 = lane_cfg_st(n_levels, cfg);
+    m->cap = capacity; m->device = device; m->cfg = cfg; m->cfg5 = lane_cfg_st(n_levels, cols, cfg);
     m->vlo = 0; m->vhi = rows - 1; m->olo = 0; m->ohi = rows - 1;
     m->frames = 0;
     *out = m;
@@ -693,8 +710,8 @@ int hsm_set_option(hsm_matcher *m, int key, int value)
             LaneCfg c;
             if (value == 0) lane_cfg(m->D, &c); else c = kLaneTable[value - 1];
             if (!lane_cfg_fits(c, m->D)) return fail(HSM_ERR_ARG, "lane config %d covers fewer than %d levels", value, m->D);
-            // 0: defaults for both families; a power-of-two entry: both families; 10..13: default family only
-            if (is_pow2(c.lpp)) { m->cfg = c; m->cfg5 = value == 0 ? lane_cfg_st(m->D, c) : c; }
+            // 0: defaults for both families; a power-of-two 8- / 16-warp entry: both families; 10..16: default family only
+            if (is_pow2(c.lpp) && value <= 9) { m->cfg = c; m->cfg5 = value == 0 ? lane_cfg_st(m->D, m->W, c) : c; }
             else m->cfg5 = c;
             m->lane_config = value; m->maps_valid = false;
             return HSM_OK;
@@ -979,25 +996,34 @@ int lbp_small_host(hsm_matcher *m, int n_frames, const void *left, const void *r
     if (m->host_stage_bytes < total) {
         if (m->host_stage) CUDA_TRY(cudaFreeHost(m->host_stage));
         m->host_stage = nullptr; m->host_stage_bytes = 0;
-        CUDA_TRY(cudaHostAlloc((void **)&m->host_stage, total, cudaHostAllocDefault));
+        CUDA_TRY(cudaHostAlloc((void **)&m->host_stage, total, cudaHostAllocMapped));
         m->host_stage_bytes = total;
     }
     char *h = m->host_stage;
     memcpy(h, left, img_bytes);
     memcpy(h + off_r, right, img_bytes);
     if (with_prior) memcpy(h + off_p, prior, prior_bytes);
-    CUDA_TRY(cudaMemcpyAsync(m->stage[0], h, img_bytes, cudaMemcpyHostToDevice, m->stream));
-    CUDA_TRY(cudaMemcpyAsync(m->stage[1], h + off_r, img_bytes, cudaMemcpyHostToDevice, m->stream));
-    if (with_prior) CUDA_TRY(cudaMemcpyAsync(m->stage[2], h + off_p, prior_bytes, cudaMemcpyHostToDevice, m->stream));
+    // A frame or two: the conversion kernel reads the page-locked block in place (mapped host memory, one PCIe round
+    // trip) instead of waiting for three copy-engine transfers of a few tens of KB each, ~7 us apiece.
+    const void *src_l = m->stage[0], *src_r = m->stage[1], *src_p = m->stage[2];
+    static const bool zero_copy_enabled = getenv("HSM_NO_ZERO_COPY") == nullptr;
+    if (zero_copy_enabled && 2 * img_bytes + prior_bytes <= ((size_t)1 << 20)) {
+        char *hd = nullptr;
+        CUDA_TRY(cudaHostGetDevicePointer((void **)&hd, h, 0));
+        src_l = hd; src_r = hd + off_r; src_p = hd + off_p;
+    } else {
+        CUDA_TRY(cudaMemcpyAsync(m->stage[0], h, img_bytes, cudaMemcpyHostToDevice, m->stream));
+        CUDA_TRY(cudaMemcpyAsync(m->stage[1], h + off_r, img_bytes, cudaMemcpyHostToDevice, m->stream));
+        if (with_prior) CUDA_TRY(cudaMemcpyAsync(m->stage[2], h + off_p, prior_bytes, cudaMemcpyHostToDevice, m->stream));
+    }
     m->frames = n_frames;
     m->have_prior = with_prior;
     m->blend.mode = with_prior ? prior_mode : kPriorNone;
     m->blend.keep32 = keep_f32;
     m->blend.keep64 = keep_f64;
     const int blocks = (int)std::min<size_t>((n + 255) / 256, (size_t)m->sm_count * 16);
-    k_convert_inputs<<<blocks, 256, 0, m->stream>>>(m->stage[0], m->stage[1], image_dtype,
-                                                    with_prior ? m->stage[2] : nullptr, prior_dtype, m->L, m->R, m->P, n,
-                                                    m->D, m->W, m->Wp);
+    k_convert_inputs<<<blocks, 256, 0, m->stream>>>(src_l, src_r, image_dtype, with_prior ? src_p : nullptr, prior_dtype,
+                                                    m->L, m->R, m->P, n, m->D, m->W, m->Wp);
     HSM_TRY(check_launch(m, "k_convert_inputs"));
     m->zero_messages = true;                                 // mrf.py:165: lbp always re-initialises
     m->labels_valid = false;

@@ -60,7 +60,7 @@ __device__ __forceinline__ unsigned long long global_ns()
 #endif
 
 template <int LPP, int VPL, int NT, bool DT_LOAD, bool FULL, bool PUSH>
-__global__ void __launch_bounds__(NT, NT == 256 ? (VPL == 1 ? HSM_TMA_MIN_BLOCKS : (VPL == 2 ? 2 : 1)) : 1)
+__global__ void __launch_bounds__(NT, NT <= 320 ? (VPL == 1 ? HSM_TMA_MIN_BLOCKS : (VPL == 2 ? 2 : 1)) : 1)
     k_iter_flow(const __grid_constant__ FlowMaps maps, Geo g, IterArgs a, FlowArgs f, int stages)
 {
     extern __shared__ __align__(1024) unsigned char smem_raw[];

@@ -91,15 +91,20 @@ struct StageLayout {
     static constexpr int DCOV = 4 * LPP * VPL;
     // The innermost TMA coordinate must be 16-byte aligned, so image segments start at a column
     // that is a multiple of 4 (up to 3 columns early) and are 4 columns longer than needed.
-    static constexpr int LBOX = PX + 4;                     // left image / prior: columns xs0 - 1 ..
-    static constexpr int RSEG = PX + DCOV + 4;              // right image: columns xs0 - DCOV .. xs0 + PX - 1
+    // (box widths are multiples of 4 elements = 16 bytes, a TMA requirement; PX is not one for the 7- and 9-warp CTAs)
+    static constexpr int PX4 = (PX + 3) / 4 * 4;
+    static constexpr int LBOX = PX4 + 4;                    // left image / prior: columns xs0 - 1 ..
+    static constexpr int RSEG = PX4 + DCOV + 4;             // right image: columns xs0 - DCOV .. xs0 + PX - 1
     static constexpr int NRB = RSEG > 256 ? 2 : 1;          // TMA boxes are at most 256 elements wide
     // two boxes: each a multiple of 32 floats so that the second one lands 128-byte aligned
     static constexpr int RBOX = NRB == 1 ? RSEG : ((RSEG / 2 + 31) / 32 * 32);
-    static constexpr unsigned align128(unsigned v) { return (v + 127u) & ~127u; }
+    __host__ __device__ static constexpr unsigned align128(unsigned v) { return (v + 127u) & ~127u; }
     static constexpr unsigned L_BYTES = align128(LBOX * 4), R_BYTES = align128(NRB * RBOX * 4),
                               P_BYTES = align128(LBOX * 4);
-    __host__ __device__ static unsigned planes_bytes(int Dp, bool dt_load) { return (dt_load ? 4u : 3u) * PX * Dp * 4u; }
+    // one plane's row segment in a stage: PX x Dp floats, padded to the 128-byte alignment bulk tensor copies need
+    // of their shared-memory address (only the 7- and 9-warp CTAs have a PX that needs padding)
+    __host__ __device__ static unsigned seg_bytes(int Dp) { return align128((unsigned)PX * (unsigned)Dp * 4u); }
+    __host__ __device__ static unsigned planes_bytes(int Dp, bool dt_load) { return (dt_load ? 4u : 3u) * seg_bytes(Dp); }
     __host__ __device__ static unsigned stage_bytes(int Dp, bool dt_load)
     {
         return planes_bytes(Dp, dt_load) + (dt_load ? 0u : (L_BYTES + R_BYTES + P_BYTES));

@@ -101,13 +101,17 @@ __device__ __forceinline__ void tmast_task(const CUtensorMap *tmW, const CUtenso
     pm.init(tid);
     const int px = pm.px;
     Lane<LPP, VPL> ln;
-    ln.init(pm.c, g.D, g.Dp, pm.seg0);
+    // a full layout (D == 4 * LPP * VPL) knows its pitch at compile time: stage sizes, slot offsets and row
+    // pitches fold into immediates instead of being rebuilt from the runtime value in every row
+    const int Dp = FULL ? 4 * LPP * VPL : g.Dp;
+    ln.init(pm.c, g.D, Dp, pm.seg0);
 
-    const unsigned row_floats = (unsigned)PX * (unsigned)g.Dp;          // one plane's row segment
-    const unsigned stage_bytes = SL::stage_bytes(g.Dp, DT_LOAD);
-    const unsigned planes_bytes = SL::planes_bytes(g.Dp, DT_LOAD);
+    const unsigned row_floats = (unsigned)PX * (unsigned)Dp;          // one plane's row segment
+    const unsigned seg_floats = SL::seg_bytes(Dp) / 4u;                  // ... padded to 128 bytes inside a stage
+    const unsigned stage_bytes = SL::stage_bytes(Dp, DT_LOAD);
+    const unsigned planes_bytes = SL::planes_bytes(Dp, DT_LOAD);
     // output staging for the TMA stores: [plane W, N, E][2 buffers] of TX pixels, 128-byte aligned
-    const unsigned ost_bytes = (((unsigned)TX * (unsigned)g.Dp * 4u) + 127u) & ~127u;
+    const unsigned ost_bytes = (((unsigned)TX * (unsigned)Dp * 4u) + 127u) & ~127u;
     unsigned char *ost = smem_raw + (size_t)stages * stage_bytes;
     float4 *exch = reinterpret_cast<float4 *>(ost + 6u * ost_bytes);
     uint64_t *full = reinterpret_cast<uint64_t *>(exch + 2 * VPL * SLOTS);
@@ -129,7 +133,7 @@ __device__ __forceinline__ void tmast_task(const CUtensorMap *tmW, const CUtenso
     const int yb0 = a.olo + by * a.band_rows;
     const int yb1 = min(yb0 + a.band_rows - 1, a.ohi);
     const size_t fplane = (size_t)frame * g.plane_stride;
-    const unsigned row_stride = (unsigned)g.W * (unsigned)g.Dp;
+    const unsigned row_stride = (unsigned)g.W * (unsigned)Dp;
     const int n_rows = yb1 - yb0 + 3;                                    // rows yb0-1 .. yb1+1
 
     const bool st_w = pm.real && px >= 2;                      // W'(y, x-1)  -> staging slot px-2
@@ -165,10 +169,10 @@ __device__ __forceinline__ void tmast_task(const CUtensorMap *tmW, const CUtenso
         if (!DT_LOAD) tx += SL::LBOX * 4u + SL::NRB * SL::RBOX * 4u + (a.has_prior ? SL::LBOX * 4u : 0u);
         mbar_expect_tx(&full[s], tx);
         tma_load_4d(dst, tmW, &full[s], 0, xs0 - 1, yy, frame_ld);
-        tma_load_4d(dst + row_floats, tmN, &full[s], 0, xs0 - 1, yy, frame_ld);
-        tma_load_4d(dst + 2 * row_floats, tmE, &full[s], 0, xs0 - 1, yy, frame_ld);
+        tma_load_4d(dst + seg_floats, tmN, &full[s], 0, xs0 - 1, yy, frame_ld);
+        tma_load_4d(dst + 2 * seg_floats, tmE, &full[s], 0, xs0 - 1, yy, frame_ld);
         if (DT_LOAD) {
-            tma_load_4d(dst + 3 * row_floats, tmD, &full[s], 0, xs0 - 1, yy, frame);
+            tma_load_4d(dst + 3 * seg_floats, tmD, &full[s], 0, xs0 - 1, yy, frame);
         } else {
             unsigned char *img = stage_ptr + planes_bytes;
             tma_load_3d(img, tmL, &full[s], xs0 - 1 - shift_l, yy, frame);
@@ -197,9 +201,9 @@ __device__ __forceinline__ void tmast_task(const CUtensorMap *tmW, const CUtenso
 
     float *Sout = a.Sout + fplane;
     // this lane's float4 slot inside a staging buffer (pixel slot 0 <-> column xs0)
-    float4 *st_wp = reinterpret_cast<float4 *>(ost) + (px - 2) * (g.Dp / 4) + ln.c;
-    float4 *st_np = reinterpret_cast<float4 *>(ost + 2u * ost_bytes) + (px - 1) * (g.Dp / 4) + ln.c;
-    float4 *st_ep = reinterpret_cast<float4 *>(ost + 4u * ost_bytes) + px * (g.Dp / 4) + ln.c;
+    float4 *st_wp = reinterpret_cast<float4 *>(ost) + (px - 2) * (Dp / 4) + ln.c;
+    float4 *st_np = reinterpret_cast<float4 *>(ost + 2u * ost_bytes) + (px - 1) * (Dp / 4) + ln.c;
+    float4 *st_ep = reinterpret_cast<float4 *>(ost + 4u * ost_bytes) + px * (Dp / 4) + ln.c;
     const unsigned ost_f4 = ost_bytes / 16u;
     auto stage_out = [&](float4 *slot, int buf, const Vec<VPL> &val) {
 #pragma unroll
@@ -225,8 +229,8 @@ __device__ __forceinline__ void tmast_task(const CUtensorMap *tmW, const CUtenso
 #pragma unroll
     for (int v = 0; v < VPL; ++v) S0.q[v] = S1.q[v] = X0.q[v] = X1.q[v] = D0.q[v] = D1.q[v] = zero4();
 
-    const unsigned lane_f4 = (unsigned)px * (unsigned)(g.Dp / 4) + (unsigned)ln.c;   // float4 index in a row segment
-    const unsigned plane_f4 = row_floats / 4;
+    const unsigned lane_f4 = (unsigned)px * (unsigned)(Dp / 4) + (unsigned)ln.c;   // float4 index in a row segment
+    const unsigned plane_f4 = seg_floats / 4;
     const float4 *lane_base = reinterpret_cast<const float4 *>(smem_raw) + lane_f4;
     // shared-space addresses of this lane's image / prior entries inside stage 0 (see data_vec_lds)
     const unsigned img_addr = smem_u32(smem_raw) + planes_bytes;
@@ -235,8 +239,9 @@ __device__ __forceinline__ void tmast_task(const CUtensorMap *tmW, const CUtenso
     const unsigned p_addr = img_addr + SL::L_BYTES + SL::R_BYTES + 4u * (unsigned)(shift_l + px);
     // element offset of (row y, this lane's pixel and chunk) inside the frame; advanced by one row per step
     // (x may be -1 or W for halo lanes: the wrap-around cancels when the neighbour offset is added)
-    unsigned row_off = (unsigned)yb0 * row_stride + (unsigned)x * (unsigned)g.Dp + 4u * (unsigned)ln.c;
+    unsigned row_off = (unsigned)yb0 * row_stride + (unsigned)x * (unsigned)Dp + 4u * (unsigned)ln.c;
 
+    const unsigned border_warp = DT_LOAD ? 0u : data_border_mask<LPP, VPL, FULL>(ln, in_x ? x : -1, g.D);
     // wait for the stage holding row y, copy this lane's chunks to registers, build the data term
     auto fetch = [&](Vec<VPL> &w, Vec<VPL> &n, Vec<VPL> &e, Vec<VPL> &d) {
         mbar_wait(&full[stage], phase);
@@ -256,7 +261,7 @@ __device__ __forceinline__ void tmast_task(const CUtensorMap *tmW, const CUtenso
         }
         if (!DT_LOAD)
             data_vec_lds<LPP, VPL, FULL>(d, ln, l_addr + stage_off, r_addr + stage_off, p_addr + stage_off,
-                                         in_x ? x : -1, g.D, a.blend, a.has_prior != 0);
+                                         in_x ? x : -1, g.D, a.blend, a.has_prior != 0, border_warp);
     };
     // every thread has copied the current stage: refill it with row index r + stages
     auto refill = [&](int r) {
@@ -271,10 +276,10 @@ __device__ __forceinline__ void tmast_task(const CUtensorMap *tmW, const CUtenso
     // peer-to-peer halo push: row `row` of a new plane also goes to the neighbouring GPU's ghost row
     // (plain stores through the peer mapping; the TMA store maps only cover this GPU's planes)
 #ifdef HSM_PUSH_PLAIN_STORES                // emergency build: per-thread peer stores instead of the bulk tensor push
-    const unsigned lane_col = (unsigned)x * (unsigned)g.Dp + 4u * (unsigned)ln.c;
+    const unsigned lane_col = (unsigned)x * (unsigned)Dp + 4u * (unsigned)ln.c;
     auto push_row = [&](float *const (&peer)[2], int row, int dx, bool mine, const Vec<VPL> &val) {
         if (!mine) return;
-        const unsigned col = lane_col + (unsigned)(dx * g.Dp);
+        const unsigned col = lane_col + (unsigned)(dx * Dp);
         if (row == a.olo && peer[0] != nullptr) store_at(peer[0], pp.off[0] + col, val);
         if (row == a.ohi && peer[1] != nullptr) store_at(peer[1], pp.off[1] + col, val);
     };
@@ -311,7 +316,7 @@ __device__ __forceinline__ void tmast_task(const CUtensorMap *tmW, const CUtenso
     // label of the pixel whose partial energy is pending: E' from staging buffer `buf`, slot of column x
     // (called by EVERY thread of the CTA: the argmin exchanges values with full-warp shuffles; a lane whose pixel
     // is not owned -- the halo column px = 0 has no slot to its left -- reads its own slot and stores nothing)
-    const int e_back = px >= 1 ? g.Dp / 4 : 0;
+    const int e_back = px >= 1 ? Dp / 4 : 0;
     auto emit_label = [&](int buf) {
         Vec<VPL> en;
 #pragma unroll
@@ -333,10 +338,7 @@ __device__ __forceinline__ void tmast_task(const CUtensorMap *tmW, const CUtenso
                     const Vec<VPL> &Din, Vec<VPL> &Dout) {
         Vec<VPL> w, n, e;
         fetch(w, n, e, Dout);
-        if (y > g.vhi) {                       // block-uniform: the row below the image sends nothing
-#pragma unroll
-            for (int v = 0; v < VPL; ++v) Sin.q[v] = zero4();
-        }
+        if (y > g.vhi) Sin = zero_vec_call<VPL>();     // block-uniform, one step per frame: the row below the image sends nothing
         // W'(y, x-1) = norm(U_W(y, x)) and S'(y+1, x) = norm(U_S(y, x)): independent of each other,
         // normalised branch-free; one warp-uniform fallback if any lane saw an out-of-range operand.
         Vec<VPL> t;
@@ -464,7 +466,7 @@ __device__ __forceinline__ void tmast_task(const CUtensorMap *tmW, const CUtenso
 }
 
 template <int LPP, int VPL, int NT, bool DT_LOAD, bool FULL, bool PUSH, bool STORE_S>
-__global__ void __launch_bounds__(NT, NT == 256 ? (VPL == 1 ? HSM_TMA_MIN_BLOCKS : (VPL == 2 ? 2 : 1)) : 1)
+__global__ void __launch_bounds__(NT, NT <= 320 ? (VPL == 1 ? HSM_TMA_MIN_BLOCKS : (VPL == 2 ? 2 : 1)) : 1)
     k_iter_tmast(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmN,
                const __grid_constant__ CUtensorMap tmE, const __grid_constant__ CUtensorMap tmD,
                const __grid_constant__ CUtensorMap tmL, const __grid_constant__ CUtensorMap tmR,

@@ -4,6 +4,10 @@
 #ifndef HSM_PUSH
 #define HSM_PUSH false
 #define HSM_FLOW_ENTRY launch_flow_any
+#define HSM_FLOW_ENTRY_B launch_flow_b
+#endif
+#ifndef HSM_ST_HALF
+#define HSM_ST_HALF 0
 #endif
 #include "matcher.hpp"
 #include "iter_flow.cuh"
@@ -19,10 +23,12 @@ int launch_flow(hsm_matcher *m, int n_iter, bool finalize, bool *launched)
     using PM = PixelMap<LPP, NT>;
     constexpr int TX = PM::PX - 2, SLOTS = PM::LANES + 2 * LPP;
     const bool dt_load = (m->data_term == 0);
+    // (layouts without the T28 variants: not launched, the caller goes on with one launch per iteration)
+    if (dt_load && !st_cfg_has_dt_load(LPP, NT)) return HSM_OK;
     const size_t stage_bytes = StageLayout<LPP, VPL, NT>::stage_bytes(m->Dp, dt_load);
     const size_t ost_bytes = ((size_t)TX * m->Dp * 4 + 127) & ~(size_t)127;
     const size_t fixed_bytes = 6 * ost_bytes + (size_t)2 * VPL * SLOTS * 16 + 128;
-    const int target_ctas = (NT == 256) ? (VPL == 1 ? 3 : 2) : (VPL == 1 ? 2 : 1);
+    const int target_ctas = tmast_ctas_per_sm(NT, VPL);
     int stages = m->stages;
     if (stages <= 0) {
         const size_t budget = (size_t)227 * 1024 / target_ctas - 1024;
@@ -97,8 +103,12 @@ int launch_flow(hsm_matcher *m, int n_iter, bool finalize, bool *launched)
                     grid, per_sm, bands, a.band_rows, strips, m->frames, smem, stages);                      \
         kernel<<<grid, NT, smem, m->stream>>>(maps, g, a, f, stages);                                        \
     } while (0)
-    if (full) { if (dt_load) HSM_LAUNCH_FLOW(true, true); else HSM_LAUNCH_FLOW(false, true); }
-    else { if (dt_load) HSM_LAUNCH_FLOW(true, false); else HSM_LAUNCH_FLOW(false, false); }
+    if constexpr (st_cfg_has_dt_load(LPP, NT)) {
+        if (full) { if (dt_load) HSM_LAUNCH_FLOW(true, true); else HSM_LAUNCH_FLOW(false, true); }
+        else { if (dt_load) HSM_LAUNCH_FLOW(true, false); else HSM_LAUNCH_FLOW(false, false); }
+    } else {
+        if (full) HSM_LAUNCH_FLOW(false, true); else HSM_LAUNCH_FLOW(false, false);
+    }
 #undef HSM_LAUNCH_FLOW
     HSM_TRY(check_launch(m, "k_iter_flow"));
     m->stats.iteration_launches++;
@@ -109,10 +119,19 @@ int launch_flow(hsm_matcher *m, int n_iter, bool finalize, bool *launched)
 
 }  // namespace
 
+#if HSM_ST_HALF == 0
 int HSM_FLOW_ENTRY(hsm_matcher *m, int n_iter, bool finalize, bool *launched)
 {
-    HSM_DISPATCH_ST(m->cfg5, { return launch_flow<LPP, VPL, NT>(m, n_iter, finalize, launched); });
+    if (!st_cfg_in_first_half(m->cfg5)) return HSM_FLOW_ENTRY_B(m, n_iter, finalize, launched);
+    HSM_DISPATCH_ST_A(m->cfg5, { return launch_flow<LPP, VPL, NT>(m, n_iter, finalize, launched); });
     return fail(HSM_ERR_ARG, "no lane configuration");
 }
+#else
+int HSM_FLOW_ENTRY_B(hsm_matcher *m, int n_iter, bool finalize, bool *launched)
+{
+    HSM_DISPATCH_ST_B(m->cfg5, { return launch_flow<LPP, VPL, NT>(m, n_iter, finalize, launched); });
+    return fail(HSM_ERR_ARG, "no lane configuration");
+}
+#endif
 
 }  // namespace hsm

@@ -4,6 +4,10 @@
 #ifndef HSM_PUSH
 #define HSM_PUSH false
 #define HSM_TMAST_ENTRY launch_tmast_any
+#define HSM_TMAST_ENTRY_B launch_tmast_b
+#endif
+#ifndef HSM_ST_HALF
+#define HSM_ST_HALF 0
 #endif
 #include "matcher.hpp"
 #include "iter_tma_st.cuh"
@@ -19,12 +23,14 @@ int launch_tmast(hsm_matcher *m, bool store_s, bool *launched)
     using PM = PixelMap<LPP, NT>;
     constexpr int TX = PM::PX - 2, SLOTS = PM::LANES + 2 * LPP;
     const bool dt_load = (m->data_term == 0);
+    // (layouts without the T28 variants: not launched, the caller falls back to the TMA-load kernel)
+    if (dt_load && !st_cfg_has_dt_load(LPP, NT)) return HSM_OK;
     const size_t stage_bytes = StageLayout<LPP, VPL, NT>::stage_bytes(m->Dp, dt_load);
     const size_t ost_bytes = ((size_t)TX * m->Dp * 4 + 127) & ~(size_t)127;
     const size_t fixed_bytes = 6 * ost_bytes + (size_t)2 * VPL * SLOTS * 16 + 128;
     int stages = m->stages;
     if (stages <= 0) {
-        const int target_ctas = (NT == 256) ? (VPL == 1 ? 3 : 2) : (VPL == 1 ? 2 : 1);
+        const int target_ctas = tmast_ctas_per_sm(NT, VPL);
         const size_t budget = (size_t)227 * 1024 / target_ctas - 1024;
         stages = 3;
         while (stages > 2 && fixed_bytes + stages * stage_bytes > budget) --stages;
@@ -34,7 +40,7 @@ int launch_tmast(hsm_matcher *m, bool store_s, bool *launched)
     HSM_TRY(ensure_maps(m));
     const Geo g = geometry(m);
     const int strips = (m->W + TX - 1) / TX;
-    IterArgs a = iter_args(m, strips, store_s, ((NT == 256) ? (VPL == 1 ? 3 : 2) : (VPL == 1 ? 2 : 1)));
+    IterArgs a = iter_args(m, strips, store_s, (tmast_ctas_per_sm(NT, VPL)));
     const int bands = (m->ohi - m->olo + 1 + a.band_rows - 1) / a.band_rows;
     dim3 grid(strips, bands, m->launch_frames);
     a.labels = store_s ? m->labels : nullptr;            // the finalising launch also writes the argmin labels
@@ -59,8 +65,12 @@ int launch_tmast(hsm_matcher *m, bool store_s, bool *launched)
                                     m->st.tmI.L, m->st.tmI.R, m->st.tmI.P, m->st.tsW[out], m->st.tsN[out],        \
                                     m->st.tsE[out], pmaps, g, a, stages));                                     \
     } while (0)
-    if (full) { if (dt_load) HSM_LAUNCH_TMAST(true, true); else HSM_LAUNCH_TMAST(false, true); }
-    else { if (dt_load) HSM_LAUNCH_TMAST(true, false); else HSM_LAUNCH_TMAST(false, false); }
+    if constexpr (st_cfg_has_dt_load(LPP, NT)) {
+        if (full) { if (dt_load) HSM_LAUNCH_TMAST(true, true); else HSM_LAUNCH_TMAST(false, true); }
+        else { if (dt_load) HSM_LAUNCH_TMAST(true, false); else HSM_LAUNCH_TMAST(false, false); }
+    } else {
+        if (full) HSM_LAUNCH_TMAST(false, true); else HSM_LAUNCH_TMAST(false, false);
+    }
 #undef HSM_LAUNCH_TMAST
     HSM_TRY(check_launch(m, "k_iter_tmast"));
     m->stats.iteration_launches++;
@@ -71,10 +81,19 @@ int launch_tmast(hsm_matcher *m, bool store_s, bool *launched)
 
 }  // namespace
 
+#if HSM_ST_HALF == 0
 int HSM_TMAST_ENTRY(hsm_matcher *m, bool store_s, bool *launched)
 {
-    HSM_DISPATCH_ST(m->cfg5, { return launch_tmast<LPP, VPL, NT>(m, store_s, launched); });
+    if (!st_cfg_in_first_half(m->cfg5)) return HSM_TMAST_ENTRY_B(m, store_s, launched);
+    HSM_DISPATCH_ST_A(m->cfg5, { return launch_tmast<LPP, VPL, NT>(m, store_s, launched); });
     return fail(HSM_ERR_ARG, "no lane configuration");
 }
+#else
+int HSM_TMAST_ENTRY_B(hsm_matcher *m, bool store_s, bool *launched)
+{
+    HSM_DISPATCH_ST_B(m->cfg5, { return launch_tmast<LPP, VPL, NT>(m, store_s, launched); });
+    return fail(HSM_ERR_ARG, "no lane configuration");
+}
+#endif
 
 }  // namespace hsm

@@ -49,7 +49,7 @@ struct LaneCfg {
 
 // Run `body` with LPP, VPL, NT as compile-time constants.
 #define HSM_DISPATCH_CASE(l, v, n, ...) \
-    if ((cfg__).lpp == l && (cfg__).vpl == v) { constexpr int LPP = l, VPL = v, NT = n; __VA_ARGS__ }
+    if ((cfg__).lpp == l && (cfg__).vpl == v && (cfg__).nt == n) { constexpr int LPP = l, VPL = v, NT = n; __VA_ARGS__ }
 #define HSM_DISPATCH(cfg, ...)                                  \
     do {                                                        \
         const hsm::LaneCfg cfg__ = (cfg);                       \
@@ -66,7 +66,9 @@ struct LaneCfg {
 
 // The default kernel family (k_iter_tmast / k_iter_flow) also has lane layouts whose lanes-per-pixel count is
 // not a power of two (PixelMap in kernels.cuh); the other families and the plane kernels only have the list above.
-#define HSM_DISPATCH_ST(cfg, ...)                               \
+// The list is compiled in two halves (launch_tmast.cu / launch_tmast_b.cu etc.: HSM_ST_HALF = 0 / 1) so that the
+// ~100 instantiations build in parallel; DT_LOAD (the T28 option) only exists for the first nine entries.
+#define HSM_DISPATCH_ST_A(cfg, ...)                             \
     do {                                                        \
         const hsm::LaneCfg cfg__ = (cfg);                       \
         HSM_DISPATCH_CASE(4, 1, 256, __VA_ARGS__)               \
@@ -75,14 +77,27 @@ struct LaneCfg {
         else HSM_DISPATCH_CASE(32, 1, 512, __VA_ARGS__)         \
         else HSM_DISPATCH_CASE(32, 2, 512, __VA_ARGS__)         \
         else HSM_DISPATCH_CASE(32, 4, 256, __VA_ARGS__)         \
-        else HSM_DISPATCH_CASE(4, 2, 256, __VA_ARGS__)          \
+    } while (0)
+#define HSM_DISPATCH_ST_B(cfg, ...)                             \
+    do {                                                        \
+        const hsm::LaneCfg cfg__ = (cfg);                       \
+        HSM_DISPATCH_CASE(4, 2, 256, __VA_ARGS__)               \
         else HSM_DISPATCH_CASE(8, 2, 256, __VA_ARGS__)          \
         else HSM_DISPATCH_CASE(16, 2, 512, __VA_ARGS__)         \
         else HSM_DISPATCH_CASE(5, 1, 256, __VA_ARGS__)          \
         else HSM_DISPATCH_CASE(6, 1, 256, __VA_ARGS__)          \
         else HSM_DISPATCH_CASE(5, 2, 256, __VA_ARGS__)          \
         else HSM_DISPATCH_CASE(6, 2, 256, __VA_ARGS__)          \
+        else HSM_DISPATCH_CASE(5, 1, 224, __VA_ARGS__)          \
+        else HSM_DISPATCH_CASE(6, 1, 288, __VA_ARGS__)          \
+        else HSM_DISPATCH_CASE(8, 1, 320, __VA_ARGS__)          \
     } while (0)
+inline bool st_cfg_in_first_half(const hsm::LaneCfg &c) { return c.vpl == 1 ? (c.lpp == 4 || c.lpp == 16 || c.lpp == 32 || (c.lpp == 8 && c.nt == 256)) : (c.lpp == 32); }
+// entries that also have the T28 (data plane) variants: power-of-two lanes, 8- or 16-warp CTAs
+constexpr bool st_cfg_has_dt_load(int lpp, int nt) { return (lpp & (lpp - 1)) == 0 && (nt == 256 || nt == 512); }
+
+// Resident CTAs per SM the default kernel family is compiled for (register budget) and sized for (shared memory)
+constexpr int tmast_ctas_per_sm(int nt, int vpl) { return nt <= 320 ? (vpl == 1 ? 3 : (vpl == 2 ? 2 : 1)) : (vpl == 1 ? 2 : 1); }
 
 struct ImageMaps {
     CUtensorMap L, R, P;
@@ -202,6 +217,10 @@ int launch_tma_push_any(hsm_matcher *m, bool store_s);                 // same, 
 int launch_tma2_any(hsm_matcher *m, bool store_s, bool *launched);
 int launch_ws_any(hsm_matcher *m, bool store_s);
 int launch_tmast_any(hsm_matcher *m, bool store_s, bool *launched);
+int launch_tmast_b(hsm_matcher *m, bool store_s, bool *launched);          // second half of the lane-layout list
+int launch_tmast_push_b(hsm_matcher *m, bool store_s, bool *launched);
+int launch_flow_b(hsm_matcher *m, int n_iter, bool finalize, bool *launched);
+int launch_flow_push_b(hsm_matcher *m, int n_iter, bool finalize, bool *launched);
 // all n_iter iterations in one persistent launch (algorithm 6); *launched = false -> caller falls back
 int launch_flow_any(hsm_matcher *m, int n_iter, bool finalize, bool *launched);
 int launch_flow_push_any(hsm_matcher *m, int n_iter, bool finalize, bool *launched);   // with neighbours attached

@@ -71,7 +71,8 @@ extern "C" {
 #define HSM_OPT_OUT_LO 5      /* ... and first/last local row this matcher owns (computes)           */
 #define HSM_OPT_OUT_HI 6
 #define HSM_OPT_STAGES 7      /* shared-memory row stages of the TMA pipeline; 0 = automatic (2..3)          */
-#define HSM_OPT_LANE_CONFIG 8 /* tuning: 0 = default lanes-per-pixel layout for n_levels, 1..9 = table entry  */
+#define HSM_OPT_LANE_CONFIG 8 /* tuning: 0 = default lanes-per-pixel layout for n_levels and width, 1..16 = table entry
+                                 (10..13: 5 / 6 lanes per pixel, 14..16: 7- / 9- / 10-warp CTAs; default kernel family only) */
 #define HSM_OPT_FRAME_GROUPS 9 /* 2 = launch every iteration as two kernels (halves of the frames) on two streams so
                                   that each fills the other's tail; 1 = one kernel; 0 = automatic (2 whenever there are >= 2 frames) */
 

@@ -43,14 +43,14 @@ def test_options_round_trip_and_validation_without_cuda(hsm):
     capi = import_module("hybrid-stereo-matching_b200._capi")
     m = hsm.StereoMRF((40, 64), 20)
     good = {capi.OPT_ALGORITHM: [0, 1, 2, 3, 4, 5, 6], capi.OPT_BAND_ROWS: [0, 7, 40], capi.OPT_DATA_TERM: [0, 1],
-            capi.OPT_STAGES: [0, 2, 3, 8], capi.OPT_LANE_CONFIG: [0, 2, 3, 10, 11, 12], capi.OPT_FRAME_GROUPS: [0, 1, 2],
+            capi.OPT_STAGES: [0, 2, 3, 8], capi.OPT_LANE_CONFIG: [0, 2, 3, 10, 11, 12, 14, 15, 16], capi.OPT_FRAME_GROUPS: [0, 1, 2],
             capi.OPT_VALID_LO: [0, 1], capi.OPT_VALID_HI: [38, 39], capi.OPT_OUT_LO: [1], capi.OPT_OUT_HI: [38]}
     for key, values in good.items():
         for value in values:
             m.set_option(key, value)
             assert m.get_option(key) == value, (key, value)
     bad = {capi.OPT_ALGORITHM: [-1, 7], capi.OPT_BAND_ROWS: [-1], capi.OPT_STAGES: [1, 9, -2],
-           capi.OPT_LANE_CONFIG: [1, 14, -1],       # entry 1 covers 16 levels only; 10..13 are the 5 / 6-lane layouts
+           capi.OPT_LANE_CONFIG: [1, 17, -1],       # entry 1 covers 16 levels only; 10..16: 5 / 6-lane layouts, other CTA widths
            capi.OPT_FRAME_GROUPS: [-1, 3], capi.OPT_VALID_LO: [-1, 40], capi.OPT_OUT_HI: [40], 99: [0]}
     for key, values in bad.items():
         for value in values:

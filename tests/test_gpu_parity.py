@@ -194,8 +194,8 @@ def test_full_size_properties_c1_batch(hsm):
     assert not planes["west"][:, :, -1].any() and not planes["east"][:, :, 0].any()
 
 
-@pytest.mark.parametrize("lane_config,max_levels", [(10, 20), (11, 24), (12, 40), (13, 48)],
-                         ids=["5x1", "6x1", "5x2", "6x2"])
+@pytest.mark.parametrize("lane_config,max_levels", [(10, 20), (11, 24), (12, 40), (13, 48), (14, 20), (15, 24), (16, 32)],
+                         ids=["5x1", "6x1", "5x2", "6x2", "5x1_7warps", "6x1_9warps", "8x1_10warps"])
 @pytest.mark.parametrize("algorithm", [5, 6], ids=["tmast", "flow"])
 def test_non_power_of_two_lane_layouts(hsm, lane_config, max_levels, algorithm):
     """Lane layouts with 5 / 6 lanes per pixel (HSM_OPT_LANE_CONFIG 10..13; chosen automatically for D = 17..24 and
