@@ -320,20 +320,28 @@ int choose_band_rows(const hsm_matcher *m, int strips, int ctas_per_sm)
     const long target = (long)m->sm_count * std::max(1, ctas_per_sm) * (grouped ? 4 : 6);
     long bands = std::max((target + per_band - 1) / per_band, (long)(rows + 63) / 64);
     bands = std::max(1L, std::min<long>(bands, std::max(1, rows / min_rows)));
+    // short frames (the shipped 80x60 / 70x60 sizes in batches): two halo rows are 13 % of a 15-row band, and the
+    // kernel is issue-bound there, so half as many bands win as long as two waves of CTAs remain
+    // (80x60xD22 x 256: 0.650 -> 0.675 of peak with 30-row bands, 0.60 with one 60-row band)
+    const long slots = (long)m->sm_count * std::max(1, ctas_per_sm);
+    while (rows <= 64 && bands >= 2 && rows / bands < 30 && per_band * (bands / 2) >= 2 * slots) bands /= 2;
     return (int)((rows + bands - 1) / bands);
 }
 
 // Persistent dataflow kernel: there is no drain per iteration and no launch per iteration, so the only costs
 // of a band are its two halo rows against the parallelism it removes.  A tile of iteration k+1 needs its
 // neighbours of iteration k, handed out one iteration's worth of tiles earlier, so an iteration must be
-// several rounds of resident CTAs long or CTAs wait: aim at ~3.5 tiles per resident CTA per iteration,
-// bands of 4..64 rows.
+// several rounds of resident CTAs long or CTAs wait: aim at ~2.25 tiles per resident CTA per iteration on one GPU
+// (640x480xD64: 16-row bands 0.815 of peak against 0.773 at 11 rows and 0.788 at 24; 960x540xD64 and 480x270xD128
+// agree, profiles/r2_probe_flow_bands.txt) and at ~3.5 with neighbours on other GPUs (the setting the row-band
+// numbers were measured with), bands of 4..64 rows.
 int choose_flow_band_rows(const hsm_matcher *m, int strips, int ctas_per_sm)
 {
     const int rows = m->ohi - m->olo + 1;
     if (m->band_rows > 0) return std::min(m->band_rows, rows);
     const long per_band = (long)strips * m->frames;
-    const long target = 7L * m->sm_count * std::max(1, ctas_per_sm) / 2;
+    const bool peers = m->peer[0].attached || m->peer[1].attached;
+    const long target = (peers ? 14L : 9L) * m->sm_count * std::max(1, ctas_per_sm) / 4;
     long bands = std::max((target + per_band - 1) / per_band, (long)(rows + 63) / 64);
     bands = std::max(1L, std::min<long>(bands, std::max(1, rows / 4)));
     return (int)((rows + bands - 1) / bands);
@@ -437,6 +445,9 @@ IterArgs iter_args(hsm_matcher *m, int strips, bool store_s, int ctas_per_sm)
     a.frame0 = m->launch_frame0;
     a.zero_in = m->zero_messages ? 1 : 0;
     a.labels = nullptr;
+    // -1 = automatic (the launch code decides per kernel); HSM_L2_HINTS overrides it for experiments
+    static const int l2_hints_env = getenv("HSM_L2_HINTS") ? atoi(getenv("HSM_L2_HINTS")) : -1;
+    a.l2_hints = l2_hints_env;
     for (int side = 0; side < 2; ++side) {
         const hsm_matcher::Peer &p = m->peer[side];
         a.pushW[side] = p.attached ? p.Wm[m->cur ^ 1] : nullptr;

@@ -72,6 +72,20 @@ __device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *map, u
         ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
 }
+// The same load with an L2 eviction-priority hint (the 64-bit policy words createpolicy.fractional produces for a
+// fraction of 1.0).  A band's first two rows are also the last two rows of the band above, which reaches them one
+// band's duration later: the first reader asks L2 to keep them (evict_last), the second one lets them go, and the
+// rows in between are streamed (evict_first) so that they do not push the kept rows out.
+constexpr uint64_t kL2EvictFirst = 0x12F0000000000000ull, kL2EvictLast = 0x14F0000000000000ull;
+__device__ __forceinline__ void tma_load_4d_hint(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2,
+                                                 int c3, uint64_t policy)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "l"(policy)
+        : "memory");
+}
 
 // Programmatic dependent launch: when the launch carries the programmatic-stream-serialization
 // attribute, the CTAs of iteration k+1 may become resident while iteration k drains and run their

@@ -18,6 +18,13 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap *map, const void 
                  ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
                  : "memory");
 }
+__device__ __forceinline__ void tma_store_4d_hint(const CUtensorMap *map, const void *src, int c0, int c1, int c2, int c3,
+                                                  uint64_t policy)
+{
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3, %4, %5}], [%1], %6;"
+                 ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "l"(policy)
+                 : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_fence() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -168,9 +175,25 @@ __device__ __forceinline__ void tmast_task(const CUtensorMap *tmW, const CUtenso
         unsigned tx = NPL * row_floats * 4u;
         if (!DT_LOAD) tx += SL::LBOX * 4u + SL::NRB * SL::RBOX * 4u + (a.has_prior ? SL::LBOX * 4u : 0u);
         mbar_expect_tx(&full[s], tx);
-        tma_load_4d(dst, tmW, &full[s], 0, xs0 - 1, yy, frame_ld);
-        tma_load_4d(dst + seg_floats, tmN, &full[s], 0, xs0 - 1, yy, frame_ld);
-        tma_load_4d(dst + 2 * seg_floats, tmE, &full[s], 0, xs0 - 1, yy, frame_ld);
+        if ((a.l2_hints & 3) != 0) {
+            // rows shared with the band above (read again by it one band later) stay in L2; the rest streams
+            const bool keep = r < 2 && yb0 > a.olo;
+            const bool shared_below = r >= n_rows - 2 && yb1 < a.ohi;
+            if (keep || shared_below || (a.l2_hints & 2) != 0) {
+                const uint64_t policy = keep ? kL2EvictLast : kL2EvictFirst;
+                tma_load_4d_hint(dst, tmW, &full[s], 0, xs0 - 1, yy, frame_ld, policy);
+                tma_load_4d_hint(dst + seg_floats, tmN, &full[s], 0, xs0 - 1, yy, frame_ld, policy);
+                tma_load_4d_hint(dst + 2 * seg_floats, tmE, &full[s], 0, xs0 - 1, yy, frame_ld, policy);
+            } else {
+                tma_load_4d(dst, tmW, &full[s], 0, xs0 - 1, yy, frame_ld);
+                tma_load_4d(dst + seg_floats, tmN, &full[s], 0, xs0 - 1, yy, frame_ld);
+                tma_load_4d(dst + 2 * seg_floats, tmE, &full[s], 0, xs0 - 1, yy, frame_ld);
+            }
+        } else {
+            tma_load_4d(dst, tmW, &full[s], 0, xs0 - 1, yy, frame_ld);
+            tma_load_4d(dst + seg_floats, tmN, &full[s], 0, xs0 - 1, yy, frame_ld);
+            tma_load_4d(dst + 2 * seg_floats, tmE, &full[s], 0, xs0 - 1, yy, frame_ld);
+        }
         if (DT_LOAD) {
             tma_load_4d(dst + 3 * seg_floats, tmD, &full[s], 0, xs0 - 1, yy, frame);
         } else {
@@ -213,7 +236,9 @@ __device__ __forceinline__ void tmast_task(const CUtensorMap *tmW, const CUtenso
     // thread 0: one bulk tensor store per plane-row; out-of-image columns are clipped by the TMA unit
     // `push` = the neighbours' ghost-row maps of the same plane: a boundary row also goes there
     auto tma_store_row = [&](const CUtensorMap *map, const CUtensorMap *push, int plane, int buf, int y) {
-        tma_store_4d(map, ost + (2u * plane + buf) * ost_bytes, 0, xs0, y - g.vlo, frame_mem);
+        // (l2_hints bit 2: the new planes are read again a whole iteration later -- let them leave L2 early)
+        if (a.l2_hints & 4) tma_store_4d_hint(map, ost + (2u * plane + buf) * ost_bytes, 0, xs0, y - g.vlo, frame_mem, kL2EvictFirst);
+        else tma_store_4d(map, ost + (2u * plane + buf) * ost_bytes, 0, xs0, y - g.vlo, frame_mem);
 #ifndef HSM_PUSH_PLAIN_STORES
         if constexpr (PUSH) {
             if (y == a.olo && pp.W[0] != nullptr) tma_store_4d(&push[0], ost + (2u * plane + buf) * ost_bytes, 0, xs0, 0, 0);

@@ -43,6 +43,7 @@ int launch_flow(hsm_matcher *m, int n_iter, bool finalize, bool *launched)
     m->launch_frame0 = 0; m->launch_frames = m->frames; m->launch_stream = m->stream;
     IterArgs a = iter_args(m, strips, false, target_ctas);
     a.band_rows = choose_flow_band_rows(m, strips, target_ctas);
+    if (a.l2_hints < 0) a.l2_hints = 0;           // (measured: the hints cost the persistent kernel 1-3 %)
     const int rows = m->ohi - m->olo + 1;
     const int bands = (rows + a.band_rows - 1) / a.band_rows;
     const size_t tiles = (size_t)m->frames * bands * strips;

@@ -242,3 +242,72 @@ def test_first_iteration_reads_no_planes_but_state_reads_back_as_zero(hsm):
                                         prior_influence_mode="adaptive", n_iter=1))
     for name, plane in want._message_field.items():
         assert np.array_equal(m._message_field[name], plane), name
+
+
+@pytest.mark.parametrize("name", ["b12_boxes_80x60_d20", "b13_checkerboard_80x60_d22", "b14_head_70x60_d27"])
+def test_shipped_small_frames_in_a_large_batch(hsm, name):
+    """The shipped down-scaled configurations as a batch of 240 frames: the 7- / 9- / 10-warp CTA shapes chosen
+    for 80- and 70-column frames, the 30-row bands of short frames and the two frame groups, every frame's labels
+    against the reference fixture (frames differ: each is the fixture's pair rolled by a few rows, and the
+    reference result of a rolled pair is not the rolled result, so only frame 0 and its copies are compared)."""
+    case = [c for c in C.HUGE_CASES if c["name"] == name][0]
+    left, right, prior, kwargs = C.case_inputs(case, 0)
+    data, meta = C.load_fixture(case)
+    n = 240
+    lefts = np.ascontiguousarray(np.broadcast_to(left, (n,) + left.shape)).copy()
+    rights = np.ascontiguousarray(np.broadcast_to(right, (n,) + right.shape)).copy()
+    priors = np.ascontiguousarray(np.broadcast_to(prior, (n,) + prior.shape)).copy()
+    # every third frame gets different content, so that a frame mix-up between CTAs cannot go unnoticed
+    lefts[1::3] = np.roll(lefts[1::3], 5, axis=1)
+    rights[1::3] = np.roll(rights[1::3], 5, axis=1)
+    matcher = hsm.StereoMRF(left.shape, case["levels"], capacity=n)
+    got = matcher.lbp_batch(lefts, rights, priors, n_iter=kwargs["n_iter"],
+                            prior_trust_factor=kwargs["prior_trust_factor"],
+                            prior_influence_mode=kwargs["prior_influence_mode"], lanes=1)
+    for frame in list(range(0, n, 3)) + list(range(2, n, 3)):
+        assert np.array_equal(got[frame], data["labels"]), frame
+    single = hsm.StereoMRF(left.shape, case["levels"])
+    want = single.lbp(lefts[1], rights[1], priors[1], n_iter=kwargs["n_iter"],
+                      prior_trust_factor=kwargs["prior_trust_factor"],
+                      prior_influence_mode=kwargs["prior_influence_mode"])
+    for frame in range(1, n, 3):
+        assert np.array_equal(got[frame], want), frame
+
+
+@pytest.mark.parametrize("hints", ["0", "1", "7"])
+def test_l2_eviction_hints_do_not_change_results(hints):
+    """HSM_L2_HINTS (read once per process, hence the subprocess) only changes cache policies of the plane loads
+    and stores of the default kernel family: same planes, same labels, with every hint on, off, and loads only."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = r"""
+import hashlib, sys
+import numpy as np
+sys.path.insert(0, %r)
+import hybrid_stereo_matching_b200 as hsm
+from importlib import import_module
+from oracle import cases as C
+capi = import_module("hybrid-stereo-matching_b200._capi")
+names = ("s16_levels32", "s14_levels22", "s18_levels64", "b02_tsukuba_crop_d32_it50", "b16_davis_d20_it10")
+todo = [c for c in C.SMALL_CASES + C.BIG_CASES + C.HUGE_CASES if c["name"] in names]
+assert len(todo) == len(names)
+for case in todo:
+    for algorithm, band_rows in ((5, 0), (5, 3), (6, 4)):
+        def make(dim, levels):
+            m = hsm.StereoMRF(tuple(dim), levels)
+            m.set_option(capi.OPT_ALGORITHM, algorithm)
+            m.set_option(capi.OPT_BAND_ROWS, band_rows)
+            return m
+        labels, planes = C.run_case(make, case)
+        data, meta = C.load_fixture(case)
+        assert np.array_equal(labels, data["labels"]), (case["name"], algorithm)
+        for name, plane in planes.items():
+            assert C.plane_sha1(plane) == meta["plane_sha1"][name], (case["name"], algorithm, name)
+print("ok")
+""" % root
+    env = dict(os.environ, HSM_L2_HINTS=hints)
+    done = subprocess.run([sys.executable, "-c", code], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                          universal_newlines=True, timeout=600)
+    assert done.returncode == 0 and done.stdout.strip().endswith("ok"), done.stdout[-2000:]
