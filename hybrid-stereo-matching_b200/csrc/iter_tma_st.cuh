@@ -101,6 +101,10 @@ __device__ __forceinline__ void tmast_task(const CUtensorMap *tmW, const CUtenso
     constexpr int TX = PX - 2;
     constexpr int SLOTS = PM::LANES + 2 * LPP;   // [0, LANES): real lanes; then a scratch pixel and a zero pixel
     constexpr int NPL = DT_LOAD ? 4 : 3;
+    // L2 eviction hints (IterArgs::l2_hints) exist only in the instantiations that gain from them: the code of the
+    // issuing thread sits on the CTA's critical path, and merely compiling the (disabled) hint branches in cost the
+    // persistent kernel 1.5-6 % and the issue-bound layouts 2-13 % (profiles/r2_probe_ab_hint_code.txt)
+    constexpr bool L2_HINTS = FULL && !FLOW && !PUSH && !DT_LOAD;
     const bool STORE_S = S_MODE == 2 ? store_s_arg : (S_MODE == 1);
 
     const int tid = threadIdx.x;
@@ -175,7 +179,7 @@ __device__ __forceinline__ void tmast_task(const CUtensorMap *tmW, const CUtenso
         unsigned tx = NPL * row_floats * 4u;
         if (!DT_LOAD) tx += SL::LBOX * 4u + SL::NRB * SL::RBOX * 4u + (a.has_prior ? SL::LBOX * 4u : 0u);
         mbar_expect_tx(&full[s], tx);
-        if ((a.l2_hints & 3) != 0) {
+        if (L2_HINTS && (a.l2_hints & 3) != 0) {
             // rows shared with the band above (read again by it one band later) stay in L2; the rest streams
             const bool keep = r < 2 && yb0 > a.olo;
             const bool shared_below = r >= n_rows - 2 && yb1 < a.ohi;
@@ -237,7 +241,7 @@ __device__ __forceinline__ void tmast_task(const CUtensorMap *tmW, const CUtenso
     // `push` = the neighbours' ghost-row maps of the same plane: a boundary row also goes there
     auto tma_store_row = [&](const CUtensorMap *map, const CUtensorMap *push, int plane, int buf, int y) {
         // (l2_hints bit 2: the new planes are read again a whole iteration later -- let them leave L2 early)
-        if (a.l2_hints & 4) tma_store_4d_hint(map, ost + (2u * plane + buf) * ost_bytes, 0, xs0, y - g.vlo, frame_mem, kL2EvictFirst);
+        if (L2_HINTS && (a.l2_hints & 4)) tma_store_4d_hint(map, ost + (2u * plane + buf) * ost_bytes, 0, xs0, y - g.vlo, frame_mem, kL2EvictFirst);
         else tma_store_4d(map, ost + (2u * plane + buf) * ost_bytes, 0, xs0, y - g.vlo, frame_mem);
 #ifndef HSM_PUSH_PLAIN_STORES
         if constexpr (PUSH) {

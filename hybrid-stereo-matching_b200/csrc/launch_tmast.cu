@@ -46,8 +46,9 @@ int launch_tmast(hsm_matcher *m, bool store_s, bool *launched)
     // data.  Worth +0.7 ... +2.2 % where the kernel is HBM-bound (240x180xD32 x 128: 0.968 -> 0.974 of peak, D = 20:
     // 0.886 -> 0.908, 640x480xD64 x 4: 0.960 -> 0.976); where it is issue-bound -- the layouts with idle chunk slots
     // -- the extra instructions of the issuing thread cost ~1 % instead (profiles/r2_probe_l2_hints.txt), so only
-    // full layouts use the hints.  (Row bands over several GPUs: not measured, off.)
-    if (a.l2_hints < 0) a.l2_hints = (!HSM_PUSH && m->D == 4 * LPP * VPL) ? 5 : 0;
+    // full layouts use the hints, and only their instantiations contain the code (tmast_task: L2_HINTS).  (Row bands
+    // over several GPUs: not measured, off.)
+    if (a.l2_hints < 0) a.l2_hints = (!HSM_PUSH && m->D == 4 * LPP * VPL && !dt_load) ? 5 : 0;
     const int bands = (m->ohi - m->olo + 1 + a.band_rows - 1) / a.band_rows;
     dim3 grid(strips, bands, m->launch_frames);
     a.labels = store_s ? m->labels : nullptr;            // the finalising launch also writes the argmin labels
