@@ -331,17 +331,17 @@ int choose_band_rows(const hsm_matcher *m, int strips, int ctas_per_sm)
 // Persistent dataflow kernel: there is no drain per iteration and no launch per iteration, so the only costs
 // of a band are its two halo rows against the parallelism it removes.  A tile of iteration k+1 needs its
 // neighbours of iteration k, handed out one iteration's worth of tiles earlier, so an iteration must be
-// several rounds of resident CTAs long or CTAs wait: aim at ~2.25 tiles per resident CTA per iteration on one GPU
-// (640x480xD64: 16-row bands 0.815 of peak against 0.773 at 11 rows and 0.788 at 24; 960x540xD64 and 480x270xD128
-// agree, profiles/r2_probe_flow_bands.txt) and at ~3.5 with neighbours on other GPUs (the setting the row-band
-// numbers were measured with), bands of 4..64 rows.
+// several rounds of resident CTAs long or CTAs wait: aim at ~3.5 tiles per resident CTA per iteration,
+// bands of 4..64 rows.  (~2.25 tiles, i.e. 16-row instead of 11-row bands at 640x480xD64, wins in short runs -- 0.92
+// against 0.89 of peak over 25 iterations -- and loses in long ones: 0.75 against 0.81 over 100 iterations, 0.84
+// against 0.85 over 200, and 0.73 against 0.79 in bench.py's 100-iteration `lbp` leg; the reference's C3 runs 100.
+// profiles/r2_probe_ab_configs.txt.)
 int choose_flow_band_rows(const hsm_matcher *m, int strips, int ctas_per_sm)
 {
     const int rows = m->ohi - m->olo + 1;
     if (m->band_rows > 0) return std::min(m->band_rows, rows);
     const long per_band = (long)strips * m->frames;
-    const bool peers = m->peer[0].attached || m->peer[1].attached;
-    const long target = (peers ? 14L : 9L) * m->sm_count * std::max(1, ctas_per_sm) / 4;
+    const long target = 7L * m->sm_count * std::max(1, ctas_per_sm) / 2;
     long bands = std::max((target + per_band - 1) / per_band, (long)(rows + 63) / 64);
     bands = std::max(1L, std::min<long>(bands, std::max(1, rows / 4)));
     return (int)((rows + bands - 1) / bands);

@@ -145,7 +145,8 @@ __global__ void __launch_bounds__(NT, NT <= 320 ? (VPL == 1 ? HSM_TMA_MIN_BLOCKS
         }
         __syncthreads();
         // the bulk tensor loads of this task (async proxy) are ordered after the acquires above
-        if (tid == 0) asm volatile("fence.proxy.async;" ::: "memory");
+        // (lane 0 of the first five warps: thread 0 issues a task's first loads and stores, warps 1..4 the later loads)
+        if ((tid & 31) == 0 && tid < 160) asm volatile("fence.proxy.async;" ::: "memory");
         const int in = (f.cur + it) & 1, out = in ^ 1;
         const bool store_s = f.finalize != 0 && it == f.n_iter - 1;
         PushPtrs pp;

@@ -105,6 +105,14 @@ __device__ __forceinline__ void tmast_task(const CUtensorMap *tmW, const CUtenso
     // issuing thread sits on the CTA's critical path, and merely compiling the (disabled) hint branches in cost the
     // persistent kernel 1.5-6 % and the issue-bound layouts 2-13 % (profiles/r2_probe_ab_hint_code.txt)
     constexpr bool L2_HINTS = FULL && !FLOW && !PUSH && !DT_LOAD;
+    // steady-state loads issued by four warps instead of thread 0 (see issue_split): +2-4 % for the persistent kernel
+    // on one frame (640x480xD64 0.844 -> 0.870 of peak), nothing for batches of full layouts, and -1.5 ... -3.5 % where
+    // the kernel is issue-bound (every warp then evaluates the dispatch: D = 22, 50, the narrow frames) --
+    // profiles/r2_probe_ab_split_issue.txt, same box, with the split compiled into every instantiation
+#ifndef HSM_SPLIT_ISSUE
+#define HSM_SPLIT_ISSUE (FLOW && FULL && !PUSH)
+#endif
+    constexpr bool SPLIT_ISSUE = HSM_SPLIT_ISSUE;
     const bool STORE_S = S_MODE == 2 ? store_s_arg : (S_MODE == 1);
 
     const int tid = threadIdx.x;
@@ -210,6 +218,58 @@ __device__ __forceinline__ void tmast_task(const CUtensorMap *tmW, const CUtenso
             if (a.has_prior) tma_load_3d(img + SL::L_BYTES + SL::R_BYTES, tmP, &full[s], xs0 - 1 - shift_l, yy, frame);
         }
     };
+    // The same loads in the steady state, dealt to lane 0 of warps 1..4 (warp 0 keeps the stores): the issuing code --
+    // ~20 instructions per bulk copy through the uniform datapath -- follows the row's barrier, and with one thread
+    // doing all of it (~130 instructions against ~230 of a row's arithmetic) warp 0 reached every barrier last.
+    // The barrier's single arrival (arrive.expect_tx with the stage's byte count) is warp 1's; a copy issued by
+    // another warp may complete before it -- the transaction count simply goes negative until then.
+    auto issue_split = [&](int r, int s) {
+        const int w = tid >> 5;
+        if ((tid & 31) != 0 || w < 1 || w > 4) return;
+        const int yy = yb0 - 1 + r - g.vlo;
+        unsigned char *stage_ptr = smem_raw + (size_t)s * stage_bytes;
+        float *dst = reinterpret_cast<float *>(stage_ptr);
+        if (w == 1) {
+            unsigned tx = NPL * row_floats * 4u;
+            if (!DT_LOAD) tx += SL::LBOX * 4u + SL::NRB * SL::RBOX * 4u + (a.has_prior ? SL::LBOX * 4u : 0u);
+            mbar_expect_tx(&full[s], tx);
+            if (L2_HINTS && (a.l2_hints & 3) != 0) {
+                const bool keep = r < 2 && yb0 > a.olo;
+                const bool shared_below = r >= n_rows - 2 && yb1 < a.ohi;
+                if (keep || shared_below || (a.l2_hints & 2) != 0)
+                    tma_load_4d_hint(dst, tmW, &full[s], 0, xs0 - 1, yy, frame_ld, keep ? kL2EvictLast : kL2EvictFirst);
+                else
+                    tma_load_4d(dst, tmW, &full[s], 0, xs0 - 1, yy, frame_ld);
+            } else {
+                tma_load_4d(dst, tmW, &full[s], 0, xs0 - 1, yy, frame_ld);
+            }
+        } else if (w == 2 || w == 3) {
+            const CUtensorMap *map = w == 2 ? tmN : tmE;
+            float *to = dst + (w == 2 ? seg_floats : 2 * seg_floats);
+            if (L2_HINTS && (a.l2_hints & 3) != 0) {
+                const bool keep = r < 2 && yb0 > a.olo;
+                const bool shared_below = r >= n_rows - 2 && yb1 < a.ohi;
+                if (keep || shared_below || (a.l2_hints & 2) != 0)
+                    tma_load_4d_hint(to, map, &full[s], 0, xs0 - 1, yy, frame_ld, keep ? kL2EvictLast : kL2EvictFirst);
+                else
+                    tma_load_4d(to, map, &full[s], 0, xs0 - 1, yy, frame_ld);
+            } else {
+                tma_load_4d(to, map, &full[s], 0, xs0 - 1, yy, frame_ld);
+            }
+        } else {
+            if (DT_LOAD) {
+                tma_load_4d(dst + 3 * seg_floats, tmD, &full[s], 0, xs0 - 1, yy, frame);
+            } else {
+                unsigned char *img = stage_ptr + planes_bytes;
+                tma_load_3d(img, tmL, &full[s], xs0 - 1 - shift_l, yy, frame);
+#pragma unroll
+                for (int b = 0; b < SL::NRB; ++b)
+                    tma_load_3d(img + SL::L_BYTES + b * SL::RBOX * 4, tmR, &full[s],
+                                xs0 - SL::DCOV - shift_r + b * SL::RBOX, yy, frame);
+                if (a.has_prior) tma_load_3d(img + SL::L_BYTES + SL::R_BYTES, tmP, &full[s], xs0 - 1 - shift_l, yy, frame);
+            }
+        }
+    };
     if (!FLOW) {
         pdl_launch_dependents();
         pdl_wait();                             // everything above overlaps the previous iteration's tail
@@ -294,7 +354,8 @@ __device__ __forceinline__ void tmast_task(const CUtensorMap *tmW, const CUtenso
     };
     // every thread has copied the current stage: refill it with row index r + stages
     auto refill = [&](int r) {
-        if (tid == 0 && r + stages < n_rows) issue(r + stages, stage);
+        if (SPLIT_ISSUE) { if (r + stages < n_rows) issue_split(r + stages, stage); }
+        else if (tid == 0 && r + stages < n_rows) issue(r + stages, stage);
         if (++stage == stages) { stage = 0; phase ^= 1u; }
     };
     auto store_at = [&](float *plane, unsigned off, const Vec<VPL> &val) {
@@ -411,9 +472,13 @@ __device__ __forceinline__ void tmast_task(const CUtensorMap *tmW, const CUtenso
         if (tid == 0) tma_store_wait_read();   // the buffers about to be reused have been read by the TMA unit
         __syncthreads();                       // the row's only CTA barrier: W' published, stage consumed
         // thread 0: refill the stage every thread has copied (row index r + stages), send this row's results
+        if (SPLIT_ISSUE) {
+            const int r = y - yb0 + 1;
+            if (r + stages < n_rows) issue_split(r + stages, stage);
+        }
         if (tid == 0) {
             const int r = y - yb0 + 1;
-            if (r + stages < n_rows) issue(r + stages, stage);
+            if (!SPLIT_ISSUE && r + stages < n_rows) issue(r + stages, stage);
             if (y <= yb1) tma_store_row(tsW, PUSH ? pmaps->W : nullptr, 0, par, y);
             if (y > yb0 + 1) {
                 tma_store_row(tsN, PUSH ? pmaps->N : nullptr, 1, par ^ 1, y - 2);
