@@ -123,8 +123,8 @@ __device__ __forceinline__ void tmast_task(const CUtensorMap *tmW, const CUtenso
     // a full layout (D == 4 * LPP * VPL) knows its pitch at compile time: stage sizes, slot offsets and row
     // pitches fold into immediates instead of being rebuilt from the runtime value in every row
     // (not in the persistent kernel with the halo push compiled in: there the constant costs 8 % -- 1080p D256 on two
-    // GPUs 0.988 -> 1.075 ms per iteration, same box, profiles/r2_probe_ab_push_flow.txt -- while it is worth 6 % to
-    // the batch kernel and 2 % to the one-GPU persistent kernel)
+    // GPUs 0.988 -> 1.075 ms per iteration, same box, profiles/r2_probe_ab_push_flow.txt -- while the other
+    // instantiations are equal or up to 2 % faster with it)
     const int Dp = (FULL && !(FLOW && PUSH)) ? 4 * LPP * VPL : g.Dp;
     ln.init(pm.c, g.D, Dp, pm.seg0);
 

@@ -3,7 +3,8 @@ import csv, re, sys
 rows = list(csv.reader(open(sys.argv[1])))
 steps = float(sys.argv[2]) if len(sys.argv) > 2 else 1.0
 hdr = rows[1]
-data = [r for r in rows[2:] if len(r) == len(hdr)]
+# (a report with several captured launches repeats the header block per launch: keep the numeric rows)
+data = [r for r in rows[2:] if len(r) == len(hdr) and r[hdr.index('Instructions Executed')].strip().isdigit()]
 ia, ie, iss = hdr.index('Source'), hdr.index('Instructions Executed'), hdr.index('Warp Stall Sampling (All Samples)')
 tot = sum(int(r[ie]) for r in data); totS = sum(int(r[iss]) for r in data)
 print("total warp instructions", tot, "per step %.1f" % (tot / steps), "samples", totS)
